@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests: golden loading and the tolerance contract."""
+import os
+
+import numpy as np
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# BASELINE.json north_star tolerances
+TOL_VERT_ABS = 1e-5     # vertices & joints, metres, absolute
+TOL_LOSS_REL = 1e-5     # losses, relative
+TOL_GRAD_REL = 1e-4     # gradients, relative (per-tensor L2 and max-norm)
+
+
+def gold(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz')))
+
+
+def T(a, grad=False, dtype=torch.float32, device='cpu'):
+    a = np.asarray(a)
+    if a.dtype.kind in 'iu':
+        return torch.tensor(a, dtype=torch.long, device=device)
+    t = torch.tensor(a, dtype=dtype, device=device)
+    return t.requires_grad_(True) if grad else t
+
+
+def npy(t):
+    return t.detach().cpu().double().numpy()
+
+
+def grad_err(g, ref):
+    """(relative L2 error, max-abs error relative to max|ref|) of a gradient tensor."""
+    g, ref = np.asarray(g, np.float64), np.asarray(ref, np.float64)
+    n = np.linalg.norm(ref)
+    l2 = np.linalg.norm(g - ref) / max(n, 1e-30)
+    mx = np.abs(g - ref).max() / max(np.abs(ref).max(), 1e-30)
+    return l2, mx
+
+
+def assert_grad(g, ref, tol=TOL_GRAD_REL, what=''):
+    l2, mx = grad_err(g, ref)
+    assert l2 <= tol and mx <= tol, '%s: grad rel-L2 %.3e, rel-max %.3e > %.1e' % (what, l2, mx, tol)
+
+
+def assert_abs(a, ref, tol, what=''):
+    e = np.abs(np.asarray(a, np.float64) - np.asarray(ref, np.float64)).max()
+    assert e <= tol, '%s: max abs err %.3e > %.1e' % (what, e, tol)
+
+
+def assert_rel(a, ref, tol, what=''):
+    a, ref = float(a), float(ref)
+    assert abs(a - ref) <= tol * max(abs(ref), 1e-30), '%s: %r vs %r (rel %.3e > %.1e)' % (
+        what, a, ref, abs(a - ref) / max(abs(ref), 1e-30), tol)
