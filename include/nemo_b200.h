@@ -1,0 +1,233 @@
+/* nemo_b200.h -- C ABI of libnemo_b200.so: the NeMo per-iteration fitting hot path on B200 (sm_100a).
+ *
+ * The reference (wangkua1/nemo-cvpr2023) is pure Python/PyTorch and defines no FFI for this path
+ * (SURVEY.md section 8(b)); its boundary is Python call sites.  This header is the C-ABI that the
+ * Python mirror of those call sites (nemo_cvpr2023_b200/) binds through ctypes; every entry point
+ * names the reference function (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions (all entry points):
+ *   - returns 0 on success, a negative NEMO_B200_E* code otherwise; text via nemo_b200_last_error()
+ *   - every tensor argument is a DEVICE pointer to contiguous row-major fp32 unless stated
+ *     (indices are int64, small tables int32); explicit sizes; the CALLER owns every buffer
+ *   - no allocation, no device synchronisation, no host reads of device data inside
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); safe under CUDA-graph capture
+ *   - "planar" vertex layout = [3][VP] per frame with VP = NEMO_B200_VP padded vertices (pad = 0)
+ */
+#ifndef NEMO_B200_H_
+#define NEMO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEMO_B200_NV 6890   /* SMPL vertices */
+#define NEMO_B200_VP 6912   /* padded to 27 x 256 */
+#define NEMO_B200_NJ 24     /* kinematic joints */
+
+#define NEMO_B200_EINVAL  (-1)  /* bad argument */
+#define NEMO_B200_ECUDA   (-2)  /* CUDA runtime error at launch */
+#define NEMO_B200_EARCH   (-3)  /* device is not sm_100 */
+
+const char* nemo_b200_last_error(void);
+int nemo_b200_version(void);
+/* compute capability (major*10+minor) of the current device, or a negative error code */
+int nemo_b200_sm_arch(void);
+
+/* ---------------------------------------------------------------- GEMM (K2 / K5)
+ * C[M,N] = epilogue( op(A)[M,K] . op(B)[K,N] ),  replaces the cuBLAS calls behind
+ *   nn.Linear in FCNN/MotionNet (nemo/neural_motion_model.py:58-71,130-148), VPoser
+ *   (human_body_prior/models/vposer_model.py:63-88), the pose-blend matmul (lbs.py:229-233),
+ *   blend_shapes (lbs.py:277-300) and their autograd backward.
+ * transA: A stored (K,M) row-major instead of (M,K).  transB: B stored (N,K) instead of (K,N).
+ * epilogue: v = acc + bias[n] (bias may be NULL); act 0 none / 1 relu / 2 leaky_relu(0.01);
+ *   if gate != NULL: v *= (gate[m*ldg+n] > 0 ? 1 : gate_slope)   (activation backward)
+ *   if accumulate: C += v else C = v. */
+int nemo_b200_gemm(const float* A, const float* B, const float* bias, float* C,
+                   int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                   int act, const float* gate, int ldg, float gate_slope, int accumulate,
+                   void* stream);
+/* same contract, always on the CUDA cores (fp32 FMA); the cross-check of the tensor-core path */
+int nemo_b200_gemm_simt(const float* A, const float* B, const float* bias, float* C,
+                        int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                        int act, const float* gate, int ldg, float gate_slope, int accumulate,
+                        void* stream);
+/* out[n] (+)= sum_m X[m*ld+n]   (bias gradients) */
+int nemo_b200_colsum(const float* X, float* out, int M, int N, int ld, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- rotations (K3)
+ * Strided addressing (all six entry points): rotation i of B sits in row n = i / per_row, slot
+ * j = i % per_row; a tensor with row stride ld (floats) and w floats per rotation is addressed at
+ * base + n*ld + w*j.  Contiguous (B,w): per_row = 1, ld = w.  This lets the kernels run in place on
+ * slices, e.g. rot6d = Y[:, :144] of the (N,147) MLP output or poses = aa[:, 3:72].
+ * rot6d: hmr/geometry.py:47-61 and vposer_model.py:32-45. */
+int nemo_b200_rot6d_fwd(const float* x6, int ld6, float* R, int ldr, int per_row, int B, void* stream);
+int nemo_b200_rot6d_bwd(const float* x6, int ld6, const float* dR, int ldr, float* dx6, int ldd,
+                        int per_row, int accumulate, int B, void* stream);
+/* rotation matrix -> axis angle: hmr/geometry.py:181-346 (nan_to_zero=1) and
+ * human_body_prior/tools/tgm_conversion.py:219-376 (nan_to_zero=0). */
+int nemo_b200_rotmat2aa_fwd(const float* R, int ldr, float* aa, int lda, int per_row, int B,
+                            int nan_to_zero, void* stream);
+int nemo_b200_rotmat2aa_bwd(const float* R, int ldr, const float* daa, int lda, float* dR, int ldd,
+                            int per_row, int accumulate, int B, int nan_to_zero, void* stream);
+/* axis angle -> rotation matrix. kind 0: quaternion form, hmr/geometry.py:9-45.
+ * kind 1: skew-matrix form, human_body_prior/body_model/lbs.py:303-334. */
+int nemo_b200_rodrigues_fwd(const float* aa, int lda, float* R, int ldr, int per_row, int B, int kind,
+                            void* stream);
+int nemo_b200_rodrigues_bwd(const float* aa, int lda, const float* dR, int ldr, float* daa, int ldd,
+                            int per_row, int accumulate, int B, int kind, void* stream);
+/* pose feature (R[1:] - I) of lbs.py:221-228 written into F[n*ldf + 0..206]; R is (N,24,9). */
+int nemo_b200_pose_feature(const float* R, float* F, int ldf, int N, void* stream);
+
+/* ---------------------------------------------------------------- kinematic chain (K6)
+ * batch_rigid_transform + transform_mat, lbs.py:337-404.  One thread per frame.
+ * R (N,24,9); J (24,3) shared (j_stride 0) or (N,24,3) (j_stride 72); parents int32[24].
+ * out: A (N,24,12) relative 3x4 transforms, JP (N,24,3) posed joints. */
+int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride, const int* parents,
+                        float* A, float* JP, int N, void* stream);
+/* dR (N,24,9) overwritten; dJ (N,24,3) overwritten when j_stride != 0, else (24,3) ACCUMULATED
+ * with atomics (caller zeroes). */
+int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents,
+                        const float* dA, const float* dJP, float* dR, float* dJ, int N, void* stream);
+
+/* ---------------------------------------------------------------- skinning (K7)
+ * lbs.py:236-252 (v_posed, T = W.A, v = T.[v_posed;1]) + the joint read-outs of smplx
+ * VertexJointSelector and hmr/smpl.py:33-36 (J_regressor_extra), fused; no per-vertex
+ * intermediate is written.  v_posed[n] = base + PO[n] (PO may be NULL).
+ *   A    (N,24,12)           PO   (N,3,VP) planar      base (3,VP) planar
+ *   Wt   (24,VP) transposed skinning weights, zero padded
+ *   W2   (VP,8,4) the same weights grouped 3 joints per float4 (4th lane 0), for the dA reduction
+ *   Jx   (nx,VP) extra joint regressor rows, zero padded (nx <= 10)
+ *   slot int8[VP]: index of the vertex in the pick list (np <= 22 unique ids) or -1
+ * out: V (N,6890,3) interleaved or NULL;  JX (N,np+nx,3): picked vertices then regressed joints. */
+int nemo_b200_skin_fwd(const float* A, const float* PO, const float* base, const float* Wt,
+                       const float* Jx, int nx, const signed char* slot, int np,
+                       float* V, float* JX, int N, void* stream);
+/* backward.  Upstream gradient of the vertices = dV (N,6890,3) [may be NULL]
+ *   + the read-outs' dJX (N,np+nx,3) [may be NULL] + sign_scale * sign bits [signs may be NULL].
+ * out: dPO (N,3,VP) overwritten (may be NULL), dA (N,24,12) overwritten.  d base = column sum of dPO. */
+int nemo_b200_skin_bwd(const float* A, const float* PO, const float* base, const float* Wt, const float* W2,
+                       const float* Jx, int nx, const signed char* slot, int np,
+                       const float* dV, const float* dJX, const uint32_t* signs, float sign_scale,
+                       float* dPO, float* dA, int N, void* stream);
+/* fused vertex-to-vertex L1 of MultiViewModel.vposer_loss (nemo/neural_motion_model.py:2792-2797):
+ * l1_sum[0] += sum_{n,v,c} | v_b - v_a |  (mesh a = "orig", carries the gradient; mesh b = detached
+ * reconstruction).  signs (N,3,2,VP/32) uint32 receives the (v_a > v_b, v_a < v_b) bit masks that
+ * nemo_b200_skin_bwd consumes, so the backward never recomputes mesh b. */
+int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const float* A_b, const float* PO_b,
+                          const float* base, const float* Wt, uint32_t* signs, float* l1_sum, int N,
+                          void* stream);
+
+/* joints49 = cat(JP, JX)[joint_map] (+ transl), hmr/smpl.py:33-37 + smplx SMPL.forward.
+ * JX rows: np picked vertices then nx regressed joints; regressed joints receive rowsum[r]*transl
+ * (they are regressed from translated vertices), all others transl.  transl may be NULL. */
+int nemo_b200_joints_gather_fwd(const float* JP, const float* JX, int nraw_x, int np,
+                                const int* joint_map, int nout, const float* transl,
+                                const float* rowsum, float* out, int N, void* stream);
+/* dJP (N,24,3), dJX (N,nraw_x,3) overwritten; dtransl (N,3) overwritten if not NULL. */
+int nemo_b200_joints_gather_bwd(const float* dout, int nraw_x, int np, const int* joint_map, int nout,
+                                const float* rowsum, float* dJP, float* dJX, float* dtransl, int N,
+                                void* stream);
+
+/* ---------------------------------------------------------------- projection + 2D loss (K7b)
+ * perspective_projection, hmr/geometry.py:78-106 (eps 0) / utils/geometry.py:63-93 (eps 1e-8).
+ * points (B,P,3), rot (B,9), trans (B,3), focal (B), centre (B,2) -> out (B,P,2). */
+int nemo_b200_project_fwd(const float* points, const float* rot, const float* trans, const float* focal,
+                          const float* centre, float eps, float* out, int B, int P, void* stream);
+int nemo_b200_project_bwd(const float* points, const float* rot, const float* trans, const float* focal,
+                          float eps, const float* dout, float* dpoints, float* drot, float* dtrans,
+                          int B, int P, void* stream);
+
+/* learned_camera_projection (nemo/neural_motion_model.py:3073-3124) + keypoint_loss (:2806-2843,
+ * GMoF nemo/utils/misc_utils.py:91-105) + the per-view reduction of step() (:3551-3558), fused.
+ *   joints (N,P,3) already translated; cameras (V,9) = [t(3), rot6d(6)]; gt (V,F,P,3) = x,y,conf;
+ *   bbox (V,F); loss_type 0 rmse 1 rmse_resized 2 mse 3 rmse_robust 4 mse_robust 5 mse_robust_resized
+ * fwd: points2d (N,P,2), loss_all (N,P,2) [rmse* modes: (N,P,1) stored in the first N*P floats],
+ *      view_acc (V,2) += {sum(loss*conf), sample count}   (caller zeroes)  */
+int nemo_b200_kp_loss_fwd(const float* joints, const int64_t* view_idx, const int64_t* frame_idx,
+                          const float* cameras, const float* gt, const float* bbox,
+                          float focal, float cx, float cy, float rho, int loss_type,
+                          float* points2d, float* loss_all, float* view_acc,
+                          int N, int P, int V, int F, void* stream);
+/* kp = mean over present views of view_sum/(count*P*comp);  dloss = upstream d(kp) (device scalar
+ * pointer, or NULL for 1.0) times `weight`.  Outputs: djoints (N,P,3) overwritten,
+ * dcam_acc (V,12) += {dt(3), dRcam(9)} (caller zeroes), loss_out[0] = kp (may be NULL). */
+int nemo_b200_kp_loss_bwd(const float* joints, const int64_t* view_idx, const int64_t* frame_idx,
+                          const float* cameras, const float* gt, const float* bbox,
+                          float focal, float cx, float cy, float rho, int loss_type,
+                          const float* view_acc, float weight,
+                          float* djoints, float* dcam_acc, float* loss_out,
+                          int N, int P, int V, int F, void* stream);
+/* dcameras (V,9) (+)= rot6d backward of the accumulated camera gradients */
+int nemo_b200_cam_finish(const float* cameras, const float* dcam_acc, float* dcameras, int accumulate,
+                         int V, void* stream);
+
+/* masked GMoF pose loss: mean(1[m>0.5] * rho^2 r^2/(r^2+rho^2)), r = pose - target
+ * (3D loss nemo/neural_motion_model.py:3870-3882, warmup :3489-3491).  target/mask gathered by
+ * (view_idx, frame_idx) from (V,F,D) / (V,F,1).  loss_acc[0] += weight-free mean; dpose (+)= weight*grad */
+int nemo_b200_pose3d_loss(const float* pose, int ldp, const int64_t* view_idx, const int64_t* frame_idx,
+                          const float* target, const float* mask, float rho, float weight,
+                          float* loss_acc, float* dpose, int ldd, int accumulate,
+                          int N, int D, int F, void* stream);
+
+/* ---------------------------------------------------------------- motion-field input (K1)
+ * frame_idx_to_raw_phase (:2978-2984) -> MonotonicNetwork.forward (monotonic_network.py:23-39) of the
+ * sample's own view -> RBF.forward (nemo/rbf.py:47-56) -> cat(instance code) (:3741-3744).
+ *   raw_phase (N) fp32; shifts, scales (V,K); centres, log_sigmas (D) (D = 0: raw warped phase is the
+ *   feature); codes (V,C) (C may be 0); noise (N,C) or NULL.
+ * out: X (N, ldx) rows [rbf(D or 1) | code(C)], warped (N) the warped phase, yn (V,3) = {y(0), y(1), den}. */
+int nemo_b200_embed_fwd(const float* raw_phase, const int64_t* view_idx,
+                        const float* shifts, const float* scales, int K,
+                        const float* centres, const float* log_sigmas, int D, int basis,
+                        const float* codes, int C, const float* noise,
+                        float* X, int ldx, float* warped, float* yn, int N, int V, void* stream);
+/* dX (N, ldx) -> dlog_sigmas (D), dshifts, dscales (V,K), dcodes (V,C): all ACCUMULATED (atomics). */
+int nemo_b200_embed_bwd(const float* raw_phase, const int64_t* view_idx,
+                        const float* shifts, const float* scales, int K,
+                        const float* centres, const float* log_sigmas, int D, int basis,
+                        int C, const float* warped, const float* yn, const float* dX, int ldx,
+                        float* dlog_sigmas, float* dshifts, float* dscales, float* dcodes,
+                        float* scratch /* (V,2) zeroed by the callee */, int N, int V, void* stream);
+/* standalone layers with the reference module semantics */
+int nemo_b200_rbf_fwd(const float* x, const float* centres, const float* log_sigmas, int D, int basis,
+                      float* out, int N, void* stream);
+int nemo_b200_rbf_bwd(const float* x, const float* centres, const float* log_sigmas, int D, int basis,
+                      const float* dout, float* dx, float* dlog_sigmas /* accumulated */, int N,
+                      void* stream);
+int nemo_b200_monotonic_fwd(const float* x, const float* shifts, const float* scales, int K,
+                            float* out, int N, void* stream);
+int nemo_b200_monotonic_bwd(const float* x, const float* shifts, const float* scales, int K,
+                            const float* dout, float* dx, float* dshifts, float* dscales /* accumulated */,
+                            float* scratch /* 2 floats, zeroed by the callee */, int N, void* stream);
+
+/* ---------------------------------------------------------------- priors
+ * MaxMixturePrior.merged_log_likelihood, hmr/smplify/prior.py:181-196.  pose rows stride ldp.
+ * ll (N) overwritten; if dpose != NULL: dpose[n] (+)= gscale * d ll[n] / d pose[n]. */
+int nemo_b200_gmm_prior(const float* pose, int ldp, const float* means, const float* precisions,
+                        const float* nll_weights, int M, int D, float* ll,
+                        float gscale, float* dpose, int ldd, int accumulate, int N, void* stream);
+/* VPoser posterior head (vposer_model.py:48-56) + KL(N(mu,sigma)||N(0,1)) of vposer_loss (:2798-2803).
+ * head (N,2L) = [mu | pre-softplus]; kl_acc[0] += sum_n sum_d KL; sigma (N,L) out (may be NULL);
+ * dhead (N,2L) = gscale * d(sum KL)/d head (may be NULL). */
+int nemo_b200_vposer_kl(const float* head, int L, float* sigma, float* kl_acc, float gscale,
+                        float* dhead, int N, void* stream);
+
+/* ---------------------------------------------------------------- optimiser
+ * torch.optim.Adam / AdamW single-tensor semantics (the reference's optimisers,
+ * nemo/neural_motion_model.py:3404-3431) over one flat parameter buffer.  `step` is the 1-based count. */
+int nemo_b200_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int decoupled, int step,
+                   const int* step_dev /* device-resident step count, overrides `step` when not NULL */,
+                   void* stream);
+int nemo_b200_increment(int* counter, void* stream);   /* *counter += 1 on the device */
+
+/* small utilities used by the host mirror */
+int nemo_b200_scale_add(float* y, const float* x, float a, size_t n, void* stream);       /* y += a*x */
+int nemo_b200_combine_losses(const float* terms, const float* weights, int n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEMO_B200_H_ */

@@ -1,0 +1,100 @@
+"""ctypes binding of libnemo_b200.so (the C ABI declared in include/nemo_b200.h).
+
+The prototypes are parsed from the header itself, so the binding cannot drift from the ABI.
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(HERE, '..', 'include', 'nemo_b200.h')
+LIB_PATH = os.path.join(HERE, 'libnemo_b200.so')
+
+_CTYPES = {'int': ctypes.c_int, 'float': ctypes.c_float, 'size_t': ctypes.c_size_t}
+
+
+def parse_header(path=HEADER):
+    """-> {name: (restype, [argtypes], [argnames])} for every function the header declares."""
+    txt = open(path).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    txt = re.sub(r'//[^\n]*', '', txt)
+    protos = {}
+    for m in re.finditer(r'(const\s+char\s*\*|int)\s+(nemo_b200_\w+)\s*\(([^)]*)\)\s*;', txt):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = ctypes.c_char_p if 'char' in ret else ctypes.c_int
+        argtypes, argnames = [], []
+        if args and args != 'void':
+            for a in args.split(','):
+                a = ' '.join(a.split())
+                nm = re.findall(r'(\w+)$', a)[0]
+                ty = a[:-len(nm)].strip()
+                if ty.endswith('*'):
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    argtypes.append(_CTYPES[ty.replace('const ', '')])
+                argnames.append(nm)
+        protos[name] = (restype, argtypes, argnames)
+    return protos
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+        self.protos = parse_header()
+
+    def load(self):
+        if self._dll is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    'libnemo_b200.so is not built (%s). Run `python -c "import __graft_entry__ as g; g.build()"` '
+                    'or `python nemo_cvpr2023_b200/build.py`. There is no CPU or PyTorch fallback.' % LIB_PATH)
+            dll = ctypes.CDLL(LIB_PATH)
+            for name, (restype, argtypes, _) in self.protos.items():
+                fn = getattr(dll, name)   # AttributeError if the .so lacks a declared symbol
+                fn.restype = restype
+                fn.argtypes = argtypes
+            self._dll = dll
+        return self._dll
+
+    def __getattr__(self, short):
+        name = 'nemo_b200_' + short
+        dll = self.load()
+        fn = getattr(dll, name)
+        names = self.protos[name][2]
+        has_stream = bool(names) and names[-1] == 'stream'
+
+        def call(*args):
+            a = [_arg(x) for x in args]
+            if has_stream:
+                a.append(torch.cuda.current_stream().cuda_stream)
+            rc = fn(*a)
+            if rc != 0:
+                raise RuntimeError('%s failed (%d): %s' % (name, rc, dll.nemo_b200_last_error().decode()))
+        call.__name__ = name
+        self.__dict__[short] = call
+        return call
+
+
+def _arg(x):
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError('nemo_b200 kernels take CUDA tensors; got a %s tensor (no CPU fallback)' % x.device)
+        if not x.is_contiguous():
+            raise RuntimeError('nemo_b200 kernels take contiguous tensors')
+        return x.data_ptr()
+    return x
+
+
+lib = _Lib()
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('nemo_cvpr2023_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
