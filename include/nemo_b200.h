@@ -144,11 +144,13 @@ int nemo_b200_project_bwd(const float* points, const float* rot, const float* tr
  * GMoF nemo/utils/misc_utils.py:91-105) + the per-view reduction of step() (:3551-3558), fused.
  *   joints (N,P,3) already translated; cameras (V,9) = [t(3), rot6d(6)]; gt (V,F,P,3) = x,y,conf;
  *   bbox (V,F); loss_type 0 rmse 1 rmse_resized 2 mse 3 rmse_robust 4 mse_robust 5 mse_robust_resized
+ *   reduction 0: step() -- mean over present views of mean(loss * conf) (:3551-3558);
+ *   reduction 1: camera_fitting_loss -- plain mean over all elements (:2845-2867)
  * fwd: points2d (N,P,2), loss_all (N,P,2) [rmse* modes: (N,P,1) stored in the first N*P floats],
  *      view_acc (V,2) += {sum(loss*conf), sample count}   (caller zeroes)  */
 int nemo_b200_kp_loss_fwd(const float* joints, const int64_t* view_idx, const int64_t* frame_idx,
                           const float* cameras, const float* gt, const float* bbox,
-                          float focal, float cx, float cy, float rho, int loss_type,
+                          float focal, float cx, float cy, float rho, int loss_type, int reduction,
                           float* points2d, float* loss_all, float* view_acc,
                           int N, int P, int V, int F, void* stream);
 /* kp = mean over present views of view_sum/(count*P*comp);  dloss = upstream d(kp) (device scalar
@@ -156,7 +158,7 @@ int nemo_b200_kp_loss_fwd(const float* joints, const int64_t* view_idx, const in
  * dcam_acc (V,12) += {dt(3), dRcam(9)} (caller zeroes), loss_out[0] = kp (may be NULL). */
 int nemo_b200_kp_loss_bwd(const float* joints, const int64_t* view_idx, const int64_t* frame_idx,
                           const float* cameras, const float* gt, const float* bbox,
-                          float focal, float cx, float cy, float rho, int loss_type,
+                          float focal, float cx, float cy, float rho, int loss_type, int reduction,
                           const float* view_acc, float weight,
                           float* djoints, float* dcam_acc, float* loss_out,
                           int N, int P, int V, int F, void* stream);
@@ -224,6 +226,8 @@ int nemo_b200_adam(float* p, const float* g, float* m, float* v, size_t n, float
 int nemo_b200_increment(int* counter, void* stream);   /* *counter += 1 on the device */
 
 /* small utilities used by the host mirror */
+/* out = dy * act'(y) for y = act(.), act 1 relu / 2 leaky_relu(0.01) */
+int nemo_b200_act_bwd(const float* dy, const float* y, float* out, size_t n, int act, void* stream);
 int nemo_b200_scale_add(float* y, const float* x, float a, size_t n, void* stream);       /* y += a*x */
 int nemo_b200_combine_losses(const float* terms, const float* weights, int n, float* out, void* stream);
 

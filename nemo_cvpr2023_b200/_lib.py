@@ -42,10 +42,15 @@ def parse_header(path=HEADER):
     return protos
 
 
+# kernels enqueued per C-ABI call when it is not exactly one
+_KERNELS_PER_CALL = {'embed_fwd': 2, 'embed_bwd': 2, 'monotonic_bwd': 2, 'last_error': 0, 'version': 0, 'sm_arch': 0}
+
+
 class _Lib:
     def __init__(self):
         self._dll = None
         self.protos = parse_header()
+        self.launches = 0   # kernels of this library launched so far (bench.py reports the delta)
 
     def load(self):
         if self._dll is None:
@@ -68,7 +73,10 @@ class _Lib:
         names = self.protos[name][2]
         has_stream = bool(names) and names[-1] == 'stream'
 
+        nk = _KERNELS_PER_CALL.get(short, 1)
+
         def call(*args):
+            self.launches += nk
             a = [_arg(x) for x in args]
             if has_stream:
                 a.append(torch.cuda.current_stream().cuda_stream)

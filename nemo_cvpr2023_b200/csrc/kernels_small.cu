@@ -351,8 +351,8 @@ __device__ __forceinline__ void load_cam(const float* __restrict__ cams, int v, 
 __global__ void k_kp_fwd(const float* __restrict__ joints, const int64_t* __restrict__ vi,
                          const int64_t* __restrict__ fi, const float* __restrict__ cams,
                          const float* __restrict__ gt, const float* __restrict__ bbox, float focal, float cx, float cy,
-                         float rho, int mode, float* __restrict__ p2d, float* __restrict__ loss_all,
-                         float* __restrict__ vacc, int N, int P, int V, int F) {
+                         float rho, int mode, int reduction, float* __restrict__ p2d,
+                         float* __restrict__ loss_all, float* __restrict__ vacc, int N, int P, int V, int F) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   int v = (int)vi[n], f = (int)fi[n];
@@ -372,7 +372,7 @@ __global__ void k_kp_fwd(const float* __restrict__ joints, const int64_t* __rest
     if (p2d) { p2d[((size_t)n * P + j) * 2] = uv[0]; p2d[((size_t)n * P + j) * 2 + 1] = uv[1]; }
     for (int k = 0; k < nc; ++k) {
       if (loss_all) loss_all[((size_t)n * P + j) * nc + k] = out[k];
-      acc += out[k] * conf;
+      acc += reduction == 0 ? out[k] * conf : out[k];
     }
   }
   atomicAdd(vacc + 2 * v, acc);
@@ -382,7 +382,7 @@ __global__ void k_kp_fwd(const float* __restrict__ joints, const int64_t* __rest
 __global__ void k_kp_bwd(const float* __restrict__ joints, const int64_t* __restrict__ vi,
                          const int64_t* __restrict__ fi, const float* __restrict__ cams,
                          const float* __restrict__ gt, const float* __restrict__ bbox, float focal, float cx, float cy,
-                         float rho, int mode, const float* __restrict__ vacc, float weight,
+                         float rho, int mode, int reduction, const float* __restrict__ vacc, float weight,
                          float* __restrict__ dj, float* __restrict__ dcam, float* __restrict__ loss_out, int N, int P,
                          int V, int F) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,16 +391,18 @@ __global__ void k_kp_bwd(const float* __restrict__ joints, const int64_t* __rest
   float kp = 0.f;
   for (int u = 0; u < V; ++u) {
     float cnt = vacc[2 * u + 1];
-    if (cnt > 0.f) { nviews++; kp += vacc[2 * u] / (cnt * P * nc); }
+    if (cnt > 0.f) { nviews++; kp += reduction == 0 ? vacc[2 * u] / (cnt * P * nc) : vacc[2 * u]; }
   }
-  if (n == 0 && loss_out) loss_out[0] = nviews ? kp / nviews : 0.f;
+  if (reduction != 0) kp /= (float)N * P * nc;
+  else kp = nviews ? kp / nviews : 0.f;
+  if (n == 0 && loss_out) loss_out[0] = kp;
   if (n >= N) return;
   int v = (int)vi[n], f = (int)fi[n];
   CamCtx c;
   load_cam(cams, v, c);
   const float* g = gt + ((size_t)v * F + f) * P * 3;
   float size = bbox ? bbox[(size_t)v * F + f] : 1.f;
-  float coef = weight / (nviews * vacc[2 * v + 1] * P * nc);
+  float coef = reduction == 0 ? weight / (nviews * vacc[2 * v + 1] * P * nc) : weight / ((float)N * P * nc);
   float gR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gt3[3] = {0, 0, 0};
   for (int j = 0; j < P; ++j) {
     size_t o = ((size_t)n * P + j) * 3;
@@ -408,7 +410,8 @@ __global__ void k_kp_bwd(const float* __restrict__ joints, const int64_t* __rest
     float uv[2], out[2], cam[3], dr[2], dc[3];
     project_point(c.R, c.t, focal, cx, cy, 0.f, p, uv, cam);
     float conf = g[j * 3 + 2];
-    float w[2] = {coef * conf, coef * conf};
+    float wc = reduction == 0 ? coef * conf : coef;
+    float w[2] = {wc, wc};
     keypoint_loss_elem(mode, uv[0] - g[j * 3], uv[1] - g[j * 3 + 1], conf > 0.5f ? 1.f : 0.f, size, rho, out, w, dr);
     project_point_bwd(cam, focal, cx, cy, 0.f, dr, dc);
 #pragma unroll
@@ -442,26 +445,26 @@ __global__ void k_cam_finish(const float* __restrict__ cams, const float* __rest
 }
 extern "C" int nemo_b200_kp_loss_fwd(const float* joints, const int64_t* view_idx, const int64_t* frame_idx,
                                      const float* cameras, const float* gt, const float* bbox, float focal, float cx,
-                                     float cy, float rho, int loss_type, float* points2d, float* loss_all,
-                                     float* view_acc, int N, int P, int V, int F, void* stream) {
+                                     float cy, float rho, int loss_type, int reduction, float* points2d,
+                                     float* loss_all, float* view_acc, int N, int P, int V, int F, void* stream) {
   NB_REQUIRE(joints && view_idx && frame_idx && cameras && gt && view_acc && N >= 0 && P > 0 && V > 0 && F > 0 &&
                  loss_type >= 0 && loss_type <= 5, "kp_loss_fwd: bad args");
   NB_REQUIRE(!(loss_type == 1 || loss_type == 5) || bbox, "kp_loss_fwd: resized loss needs bbox");
   if (N == 0) return 0;
-  k_kp_fwd<<<NB_1D(N)>>>(joints, view_idx, frame_idx, cameras, gt, bbox, focal, cx, cy, rho, loss_type, points2d,
-                         loss_all, view_acc, N, P, V, F);
+  k_kp_fwd<<<NB_1D(N)>>>(joints, view_idx, frame_idx, cameras, gt, bbox, focal, cx, cy, rho, loss_type, reduction,
+                         points2d, loss_all, view_acc, N, P, V, F);
   NB_LAUNCH_CHECK("kp_loss_fwd");
 }
 extern "C" int nemo_b200_kp_loss_bwd(const float* joints, const int64_t* view_idx, const int64_t* frame_idx,
                                      const float* cameras, const float* gt, const float* bbox, float focal, float cx,
-                                     float cy, float rho, int loss_type, const float* view_acc, float weight,
-                                     float* djoints, float* dcam_acc, float* loss_out, int N, int P, int V, int F,
-                                     void* stream) {
+                                     float cy, float rho, int loss_type, int reduction, const float* view_acc,
+                                     float weight, float* djoints, float* dcam_acc, float* loss_out, int N, int P,
+                                     int V, int F, void* stream) {
   NB_REQUIRE(joints && view_idx && frame_idx && cameras && gt && view_acc && djoints && N >= 0 && P > 0 && V > 0 &&
                  F > 0 && loss_type >= 0 && loss_type <= 5, "kp_loss_bwd: bad args");
   if (N == 0) return 0;
-  k_kp_bwd<<<NB_1D(N)>>>(joints, view_idx, frame_idx, cameras, gt, bbox, focal, cx, cy, rho, loss_type, view_acc,
-                         weight, djoints, dcam_acc, loss_out, N, P, V, F);
+  k_kp_bwd<<<NB_1D(N)>>>(joints, view_idx, frame_idx, cameras, gt, bbox, focal, cx, cy, rho, loss_type, reduction,
+                         view_acc, weight, djoints, dcam_acc, loss_out, N, P, V, F);
   NB_LAUNCH_CHECK("kp_loss_bwd");
 }
 extern "C" int nemo_b200_cam_finish(const float* cameras, const float* dcam_acc, float* dcameras, int accumulate,
@@ -909,6 +912,17 @@ extern "C" int nemo_b200_scale_add(float* y, const float* x, float a, size_t n, 
   if (n == 0) return 0;
   k_scale_add<<<cdiv((long long)n, 256), 256, 0, S(stream)>>>(y, x, a, n);
   NB_LAUNCH_CHECK("scale_add");
+}
+__global__ void k_act_bwd(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ out, size_t n,
+                          float slope) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dy[i] * (y[i] > 0.f ? 1.f : slope);
+}
+extern "C" int nemo_b200_act_bwd(const float* dy, const float* y, float* out, size_t n, int act, void* stream) {
+  NB_REQUIRE(dy && y && out && (act == 1 || act == 2), "act_bwd: bad args");
+  if (n == 0) return 0;
+  k_act_bwd<<<cdiv((long long)n, 256), 256, 0, S(stream)>>>(dy, y, out, n, act == 1 ? 0.f : 0.01f);
+  NB_LAUNCH_CHECK("act_bwd");
 }
 __global__ void k_combine(const float* __restrict__ t, const float* __restrict__ w, int n, float* __restrict__ out) {
   float s = 0.f;

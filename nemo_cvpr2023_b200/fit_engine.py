@@ -1,0 +1,465 @@
+"""Hand-scheduled forward + backward + Adam of one NeMo fitting iteration on one GPU.
+
+This is the engine behind `nemo.neural_motion_model.NemoV1..V4.step / get_preds_batch / warmup /
+opt_cam`.  It replaces the autograd graph of ~15.6k ATen calls the reference builds per step
+ with ~90 launches of the kernels in libnemo_b200.so on preallocated buffers;
+nothing here runs on the CPU and no per-vertex intermediate is written to HBM.
+
+Reference semantics reproduced (paths under /root/reference, file nemo/neural_motion_model.py unless noted):
+  get_preds_batch :3637-3672 (V4 :3968-4008), get_preds_given_phases_and_view :3733-3781 / :3911-3956,
+  _get_smpl_given_poses :2963-2976, learned_camera_projection :3073-3124, keypoint_loss :2806-2843,
+  per-view reduction :3551-3558, vposer_loss :2775-2804, gmm_prior_loss :2758-2773, 3D loss :3870-3882,
+  instance loss :3864-3867, optimisers :3404-3431 / :3694-3721, warmup :3455-3509, opt_cam :2869-2906 / :4060-4149.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import assets
+from ._lib import lib, require_cuda
+from .functional import KP_LOSSES, NV, RBF_BASES, VP, SMPLConstants, gemm
+
+H_VP = 512     # VPoser hidden width
+L_VP = 32      # VPoser latent size
+
+
+class ParamGroup:
+    """One optimiser of the reference = one flat fp32 buffer (+ grad, Adam moments, device step count)."""
+
+    def __init__(self, specs, device, lr, weight_decay=0.0, decoupled=False):
+        self.specs = specs                      # [(name, shape)]
+        n = sum(int(np.prod(s)) for _, s in specs)
+        self.p = torch.zeros(n, device=device)
+        self.g = torch.zeros(n, device=device)
+        self.m = torch.zeros(n, device=device)
+        self.v = torch.zeros(n, device=device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.lr, self.wd, self.decoupled = float(lr), float(weight_decay), bool(decoupled)
+        self.betas, self.eps = (0.9, 0.999), 1e-8
+        self.views, self.gviews, self.offsets = {}, {}, {}
+        o = 0
+        for name, shape in specs:
+            k = int(np.prod(shape))
+            self.views[name] = self.p[o:o + k].view(shape)
+            self.gviews[name] = self.g[o:o + k].view(shape)
+            self.offsets[name] = (o, k)
+            o += k
+
+    def adam_step(self):
+        lib.increment(self.step_dev)
+        lib.adam(self.p, self.g, self.m, self.v, self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                 self.wd, int(self.decoupled), 0, self.step_dev)
+
+
+def fold_vposer(sd, device):
+    """Eval-mode VPoser (human_body_prior/models/vposer_model.py:63-88, model_loader.py:83) as plain
+    affine maps: BatchNorm1d running statistics are folded into the neighbouring Linear layers, and the
+    activation-free chain Linear(512,512) -> Linear(512,512) -> {mu, logvar} is merged into one 512->64
+    map (computed in float64).  Weights are frozen (model_loader.py:65-67) so this is done once."""
+    g = lambda k: torch.as_tensor(np.asarray(sd[k]), dtype=torch.float64)
+    eps = 1e-5
+    s1 = g('encoder_net.1.weight') / torch.sqrt(g('encoder_net.1.running_var') + eps)
+    o1 = g('encoder_net.1.bias') - g('encoder_net.1.running_mean') * s1
+    W1, b1 = g('encoder_net.2.weight'), g('encoder_net.2.bias')
+    W1f, b1f = W1 * s1[None], b1 + W1 @ o1
+    s2 = g('encoder_net.4.weight') / torch.sqrt(g('encoder_net.4.running_var') + eps)
+    o2 = g('encoder_net.4.bias') - g('encoder_net.4.running_mean') * s2
+    W6, b6 = g('encoder_net.6.weight'), g('encoder_net.6.bias')
+    W6f, b6f = W6 * s2[None], b6 + W6 @ o2
+    W7, b7 = g('encoder_net.7.weight'), g('encoder_net.7.bias')
+    Wh = torch.cat([g('encoder_net.8.mu.weight'), g('encoder_net.8.logvar.weight')], 0)
+    bh = torch.cat([g('encoder_net.8.mu.bias'), g('encoder_net.8.logvar.bias')], 0)
+    Whf = Wh @ W7 @ W6f
+    bhf = Wh @ (W7 @ b6f + b7) + bh
+    f = lambda t: t.float().to(device).contiguous()
+    return dict(W1=f(W1f), b1=f(b1f), Wh=f(Whf), bh=f(bhf),
+                Wd0=f(g('decoder_net.0.weight')), bd0=f(g('decoder_net.0.bias')),
+                Wd3=f(g('decoder_net.3.weight')), bd3=f(g('decoder_net.3.bias')),
+                Wd5=f(g('decoder_net.5.weight')), bd5=f(g('decoder_net.5.bias')))
+
+
+class FitEngine:
+    def __init__(self, args, num_views, num_frames, smpl_consts: SMPLConstants, vposer_sd, gmm, data,
+                 version=2, device='cuda', init_params=None, focal=assets.FOCAL_LENGTH):
+        require_cuda()
+        self.args, self.V, self.F, self.C_, self.version = args, int(num_views), int(num_frames), smpl_consts, version
+        self.dev = torch.device(device)
+        a = args
+        self.h = int(a.h_dim)
+        self.D = int(a.phase_rbf_dim) if version >= 2 else 0
+        self.Cc = int(a.instance_code_size)
+        self.K = int(a.monotonic_network_n_nodes)
+        self.in_dim = (self.D if self.D > 0 else 1) + self.Cc
+        self.basis = RBF_BASES.index(a.rbf_kernel) if self.D > 0 else 1
+        self.focal = float(focal)
+        self.IMG_D0, self.IMG_D1 = int(data['IMG_D0']), int(data['IMG_D1'])
+        h, V, K = self.h, self.V, self.K
+        # ---- parameters, grouped as the reference groups its optimisers
+        self.g_cam = ParamGroup([('learned_cameras', (V, 9))], self.dev, a.lr_camera)
+        motion = [('learned_motion.net.net.0.weight', (h, self.in_dim)), ('learned_motion.net.net.0.bias', (h,)),
+                  ('learned_motion.net.net.2.weight', (h, h)), ('learned_motion.net.net.2.bias', (h,)),
+                  ('learned_motion.net.net.4.weight', (h, h)), ('learned_motion.net.net.4.bias', (h,)),
+                  ('learned_motion.rot_out.weight', (144, h)), ('learned_motion.linear_out.weight', (3, h)),
+                  ('learned_motion.rot_out.bias', (144,)), ('learned_motion.linear_out.bias', (3,))]
+        if self.D > 0:
+            motion.append(('phase_rbf.log_sigmas', (self.D,)))
+        self.g_motion = ParamGroup(motion, self.dev, a.lr_human, a.wd_human, decoupled=(a.opt_human == 'adamw'))
+        self.g_phase = ParamGroup([('shifts', (V, K)), ('scales', (V, K))], self.dev, a.lr_phase)
+        self.g_inst = ParamGroup([('learned_instance_code', (V, self.Cc))], self.dev, a.lr_instance) if self.Cc else None
+        self.betas = torch.zeros(1, 10, device=self.dev)
+        self.betas_grad = torch.zeros(1, 10, device=self.dev)
+        self.compute_betas_grad = False
+        self.centres = torch.linspace(0, 1, max(self.D, 1), device=self.dev)
+        mv = self.g_motion.views
+        o0 = self.g_motion.offsets['learned_motion.rot_out.weight'][0]
+        self.Whead = self.g_motion.p[o0:o0 + 147 * h].view(147, h)
+        self.gWhead = self.g_motion.g[o0:o0 + 147 * h].view(147, h)
+        o1 = self.g_motion.offsets['learned_motion.rot_out.bias'][0]
+        self.bhead = self.g_motion.p[o1:o1 + 147]
+        self.gbhead = self.g_motion.g[o1:o1 + 147]
+        if init_params is not None:
+            self.load_params(init_params)
+        # ---- frozen priors and data
+        self.vp = fold_vposer(vposer_sd, self.dev)
+        f32 = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.dev).contiguous()
+        self.gmm_means, self.gmm_prec, self.gmm_w = f32(gmm['means']), f32(gmm['precisions']), f32(gmm['nll_weights']).reshape(-1)
+        self.gt2d = f32(data['points2d_gt_all'])
+        self.bbox = f32(data['gt_bbox_size'])
+        self.hmr_theta = f32(data['hmr_theta']) if 'hmr_theta' in data else None
+        self.hmr_mask = f32(data['hmr_mask']) if 'hmr_mask' in data else None
+        self.phase_table = torch.linspace(0, 1, self.F, device=self.dev)
+        # ---- read-outs the losses need (SURVEY.md section 8(a) "which joints the losses consume")
+        jm = np.asarray(assets.JOINT_MAP_49)
+        sel = list(range(25)) if version >= 4 else [38] + list(range(1, 25))
+        raw = jm[sel]
+        picks = sorted({int(r) - 24 for r in raw if 24 <= r < 45})
+        extras = sorted({int(r) - 45 for r in raw if r >= 45})
+        vids = np.asarray(assets.VERTEX_JOINT_IDS)[picks]
+        self.ro = smpl_consts.make_readout(vids, smpl_consts.raw['J_regressor_extra'][extras].cpu() if extras
+                                           else torch.zeros(0, NV))
+        m25 = []
+        for r in raw:
+            r = int(r)
+            m25.append(r if r < 24 else (24 + picks.index(r - 24) if r < 45 else 24 + len(picks) + extras.index(r - 45)))
+        self.map25 = torch.tensor(m25, dtype=torch.int32, device=self.dev)
+        self._ws = {}
+        self.training = False
+
+    # ------------------------------------------------------------------ parameters
+    def named_params(self):
+        out = dict(self.g_cam.views)
+        out.update(self.g_motion.views)
+        for v in range(self.V):
+            out['phase_networks.%d.shifts' % v] = self.g_phase.views['shifts'][v]
+            out['phase_networks.%d.scales' % v] = self.g_phase.views['scales'][v]
+        if self.g_inst:
+            out.update(self.g_inst.views)
+        out['learned_betas'] = self.betas
+        return out
+
+    def named_grads(self):
+        out = dict(self.g_cam.gviews)
+        out.update(self.g_motion.gviews)
+        for v in range(self.V):
+            out['phase_networks.%d.shifts' % v] = self.g_phase.gviews['shifts'][v]
+            out['phase_networks.%d.scales' % v] = self.g_phase.gviews['scales'][v]
+        if self.g_inst:
+            out.update(self.g_inst.gviews)
+        out['learned_betas'] = self.betas_grad
+        return out
+
+    def load_params(self, params):
+        mine = self.named_params()
+        for k, v in params.items():
+            if k == 'phase_rbf.centres':
+                self.centres.copy_(torch.as_tensor(np.asarray(v), dtype=torch.float32).reshape(-1))
+            elif k in mine:
+                mine[k].copy_(torch.as_tensor(np.asarray(v), dtype=torch.float32).reshape(mine[k].shape))
+
+    def groups(self):
+        return [g for g in (self.g_cam, self.g_motion, self.g_phase, self.g_inst) if g is not None]
+
+    # ------------------------------------------------------------------ workspace
+    def ws(self, N):
+        if N in self._ws:
+            return self._ws[N]
+        d, h = self.dev, self.h
+        Np = N + 1
+        z = lambda *s: torch.zeros(*s, device=d)
+        nxr = self.ro['np'] + self.ro['nx']
+        w = dict(
+            raw=z(N), X=z(Np, self.in_dim), warped=z(N), yn=z(self.V, 3),
+            H1=z(Np, h), H2=z(Np, h), H3=z(Np, h), Y=z(Np, 147),
+            R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, 207),
+            PO_m=z(N, 3 * VP), PO_o=z(N, 3 * VP), PO_r=z(N, 3 * VP), dPO=z(N, 3 * VP),
+            A_m=z(N, 288), A_o=z(N, 288), A_r=z(N, 288), JP=z(N, 72), JPs=z(N, 72),
+            R_o=z(N, 24, 9), R_r=z(N, 24, 9),
+            JX=z(N, max(nxr, 1), 3), j25=z(N, 25, 3), p2d=z(N, 25, 2), loss_all=z(N, 25, 2), view_acc=z(self.V, 2),
+            E1=z(N, H_VP), head=z(N, 2 * L_VP), dhead=z(N, 2 * L_VP), D1=z(N, H_VP), D2=z(N, H_VP), D3=z(N, 126),
+            Rdec=z(N * 21, 9), recon=z(N, 69), signs=torch.zeros(N, 3, 2, VP // 32, dtype=torch.int32, device=d),
+            ll=z(N), acc=z(8), terms=z(8), wts=z(8), total=z(1),
+            d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
+            dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, 147), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.in_dim),
+            dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dbase=z(3 * VP),
+            base=z(3, VP), J=z(72), vi=torch.zeros(N, dtype=torch.long, device=d),
+            fi=torch.zeros(N, dtype=torch.long, device=d), noise=z(N, max(self.Cc, 1)),
+        )
+        self._ws[N] = w
+        return w
+
+    # ------------------------------------------------------------------ forward pieces
+    def _shape(self, w):
+        """v_shaped and rest joints for the shared betas (blend_shapes + vertices2joints, lbs.py:257-300)."""
+        C = self.C_
+        gemm(self.betas, C.Sp, w['base'], 1, 3 * VP, 10, 10, 3 * VP, 3 * VP, bias=C.vt.view(-1))
+        gemm(self.betas, C.JSt, w['J'], 1, 72, 10, 10, 72, 72, bias=C.Jt)
+
+    def _motion_forward(self, w, N, view_idx, raw_phase, use_noise):
+        mv, gp, C = self.g_motion.views, self.g_phase.views, self.Cc
+        Np, h = N + 1, self.h
+        codes = self.g_inst.views['learned_instance_code'] if self.g_inst else None
+        noise = None
+        if use_noise:
+            w['noise'].normal_().mul_(float(self.args.code_noise))
+            noise = w['noise']
+        lib.embed_fwd(raw_phase, view_idx, gp['shifts'], gp['scales'], self.K, self.centres,
+                      mv['phase_rbf.log_sigmas'] if self.D > 0 else None, self.D, self.basis, codes, C, noise,
+                      w['X'], self.in_dim, w['warped'], w['yn'], N, self.V)
+        W = lambda i: mv['learned_motion.net.net.%d.weight' % i]
+        b = lambda i: mv['learned_motion.net.net.%d.bias' % i]
+        gemm(w['X'], W(0), w['H1'], Np, h, self.in_dim, self.in_dim, self.in_dim, h, transB=True, bias=b(0), act=1)
+        gemm(w['H1'], W(2), w['H2'], Np, h, h, h, h, h, transB=True, bias=b(2), act=1)
+        # FCNN's last Linear followed by MotionNet.relu (:132)
+        gemm(w['H2'], W(4), w['H3'], Np, h, h, h, h, h, transB=True, bias=b(4), act=1)
+        gemm(w['H3'], self.Whead, w['Y'], Np, 147, h, h, h, 147, transB=True, bias=self.bhead)
+        lib.rot6d_fwd(w['Y'], 147, w['R'], 216, 24, N * 24)
+        lib.rotmat2aa_fwd(w['R'], 9, w['aa'], 3, 1, N * 24, 1)
+        # trans - trans_0 (:3755-3766): row N of Y is the phase-0 / zero-code sample
+        torch.sub(w['Y'][:N, 144:147], w['Y'][N:Np, 144:147], out=w['trans'])
+
+    def _lbs_forward(self, w, N, R, PO, A, JP):
+        C = self.C_
+        lib.pose_feature(R, w['F'], 207, N)
+        gemm(w['F'], C.PD, PO, N, 3 * VP, 207, 207, 3 * VP, 3 * VP)
+        lib.chain_fwd(R, w['J'], 0, C.parents, A, JP, N)
+
+    # ------------------------------------------------------------------ the step
+    def forward_backward(self, view_idx, frame_idx, update=True, phases=None, mode='step', detach_pose=False):
+        """mode: 'step' (all losses), 'warmup' (3D pose loss only), 'opt_cam' (V4: 2D + 3D, pose detached),
+        'cam_fit' (MultiViewModel.opt_cam: plain-mean reprojection loss only)."""
+        a, C, ro = self.args, self.C_, self.ro
+        N = int(view_idx.shape[0])
+        w = self.ws(N)
+        Np, h = N + 1, self.h
+        w['vi'].copy_(view_idx, non_blocking=True)
+        w['fi'].copy_(frame_idx, non_blocking=True)
+        vi, fi = w['vi'], w['fi']
+        if phases is None:
+            torch.index_select(self.phase_table, 0, fi, out=w['raw'])
+        else:
+            w['raw'].copy_(phases)
+        w['acc'].zero_()
+        w['view_acc'].zero_()
+        use_noise = self.version >= 3 and self.training and a.code_noise > 0 and self.Cc > 0
+        self._motion_forward(w, N, vi, w['raw'], use_noise)
+        self._shape(w)
+        full = mode == 'step'
+        need_2d = mode in ('step', 'opt_cam', 'cam_fit')
+        mode_id = KP_LOSSES.index(a.loss)
+        red = 1 if mode == 'cam_fit' else 0
+        cx, cy = float(self.IMG_D0 // 2), float(self.IMG_D1 // 2)   # (:3104-3106) height/2 is used as cx
+        acc = w['acc']   # 0 l1_sum, 1 kl_sum, 2 loss_3d, 3 gmm_sum, 4 kp, 5 instance
+        if need_2d:
+            self._lbs_forward(w, N, w['R'], w['PO_m'], w['A_m'], w['JP'])
+            lib.skin_fwd(w['A_m'], w['PO_m'], w['base'], C.Wt, ro['Jx'] if ro['nx'] else None, ro['nx'],
+                         ro['slot'] if ro['np'] else None, ro['np'], None, w['JX'], N)
+            lib.joints_gather_fwd(w['JP'], w['JX'], ro['np'] + ro['nx'], ro['np'], self.map25, 25, w['trans'], None,
+                                  w['j25'], N)
+            lib.kp_loss_fwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox, self.focal,
+                            cx, cy, 100.0, mode_id, red, w['p2d'], w['loss_all'], w['view_acc'], N, 25, self.V, self.F)
+        w_vp = float(a.weight_vp_loss) if full else 0.0
+        w_kl = float(a.weight_vp_z_loss) if full else 0.0
+        w_gmm = float(a.weight_gmm_loss) if full else 0.0
+        w_3d = float(getattr(a, 'weight_3d_loss', 0.0)) if (self.version >= 3 and mode in ('step', 'opt_cam')) else 0.0
+        if mode == 'warmup':
+            w_3d = 1.0
+        w_inst = float(getattr(a, 'weight_instance_loss', 0.0)) if (self.version >= 3 and full and self.Cc) else 0.0
+        w['d_aa'].zero_()
+        if full:
+            vp = self.vp
+            # VPoser encode (mean) -> decode (:2779-2784)
+            gemm(w['aa'].view(-1)[3:], vp['W1'], w['E1'], N, H_VP, 63, 72, 63, H_VP, transB=True, bias=vp['b1'], act=2)
+            gemm(w['E1'], vp['Wh'], w['head'], N, 2 * L_VP, H_VP, H_VP, H_VP, 2 * L_VP, transB=True, bias=vp['bh'])
+            lib.vposer_kl(w['head'], L_VP, None, acc[1:2], w_kl / N, w['dhead'], N)
+            gemm(w['head'], vp['Wd0'], w['D1'], N, H_VP, L_VP, 2 * L_VP, L_VP, H_VP, transB=True, bias=vp['bd0'], act=2)
+            gemm(w['D1'], vp['Wd3'], w['D2'], N, H_VP, H_VP, H_VP, H_VP, H_VP, transB=True, bias=vp['bd3'], act=2)
+            gemm(w['D2'], vp['Wd5'], w['D3'], N, 126, H_VP, H_VP, H_VP, 126, transB=True, bias=vp['bd5'])
+            lib.rot6d_fwd(w['D3'], 6, w['Rdec'], 9, 1, N * 21)
+            lib.rotmat2aa_fwd(w['Rdec'], 189, w['recon'], 69, 21, N * 21, 0)
+            w['recon'][:, 63:].copy_(w['aa'][:, 66:72])
+            # the two extra SMPL forwards of vposer_loss (:2787-2793): quaternion Rodrigues, shared global orient
+            for key_R, src, ld in (('R_o', w['aa'].view(-1)[3:], 72), ('R_r', w['recon'], 69)):
+                Rb = w[key_R]
+                Rb[:, 0].copy_(w['R'][:, 0])
+                lib.rodrigues_fwd(src, ld, Rb.view(-1)[9:], 216, 23, N * 23, 0)
+            self._lbs_forward(w, N, w['R_o'], w['PO_o'], w['A_o'], w['JPs'])
+            self._lbs_forward(w, N, w['R_r'], w['PO_r'], w['A_r'], w['JPs'])
+            lib.skin_l1_fwd(w['A_o'], w['PO_o'], w['A_r'], w['PO_r'], w['base'], C.Wt, w['signs'], acc[0:1], N)
+            # GMM prior (:2758-2773): value and (scaled) gradient in one pass
+            lib.gmm_prior(w['aa'].view(-1)[3:], 72, self.gmm_means, self.gmm_prec, self.gmm_w, self.gmm_means.shape[0],
+                          69, w['ll'], w_gmm / N, w['d_aa'].view(-1)[3:] if update else None, 72, 1, N)
+            lib.colsum(w['ll'], acc[3:4], N, 1, 1, 1)
+        if w_3d or (self.version >= 3 and full and getattr(a, 'weight_3d_loss', 0.0)):
+            lib.pose3d_loss(w['aa'].view(-1)[3:], 72, vi, fi, self.hmr_theta, self.hmr_mask, 100.0, w_3d, acc[2:3],
+                            w['d_aa'].view(-1)[3:] if update else None, 72, 1, N, 69, self.F)
+        if w_inst:
+            code = self.g_inst.views['learned_instance_code']
+            acc[5:6].copy_((code * code).mean().reshape(1))
+
+        # ---------------------------------------------------------------- backward
+        if update:
+            for g in self.groups():
+                g.g.zero_()
+            dR = w['dR']
+            if need_2d:
+                lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox,
+                                self.focal, cx, cy, 100.0, mode_id, red, w['view_acc'], 1.0, w['dj25'], w['dcam'].zero_(),
+                                acc[4:5], N, 25, self.V, self.F)
+                lib.cam_finish(self.g_cam.views['learned_cameras'], w['dcam'], self.g_cam.gviews['learned_cameras'],
+                               0, self.V)
+                lib.joints_gather_bwd(w['dj25'], ro['np'] + ro['nx'], ro['np'], self.map25, 25, None, w['dJP'],
+                                      w['dJX'], w['dtr'], N)
+                if detach_pose:
+                    # V4 opt_cam (:4060-4149): body rotmats detached, gradient reaches the MLP through the global
+                    # orientation and the translation only
+                    pass
+                lib.skin_bwd(w['A_m'], w['PO_m'], w['base'], C.Wt, C.W2, ro['Jx'] if ro['nx'] else None, ro['nx'],
+                             ro['slot'] if ro['np'] else None, ro['np'], None, w['dJX'], None, 0.0, w['dPO'],
+                             w['dA'], N)
+                lib.chain_bwd(w['R'], w['J'], 0, C.parents, w['dA'], w['dJP'], dR, w['dJ'].zero_(), N)
+                if not detach_pose:
+                    gemm(w['dPO'], C.PD, dR.view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
+                         accumulate=True)
+                else:
+                    dR[:, 1:].zero_()
+                if self.compute_betas_grad:
+                    self._betas_grad(w, N, first=True)
+            else:
+                dR.zero_()
+                w['dtr'].zero_()
+            if full and w_kl:
+                vp = self.vp
+                gemm(w['dhead'], vp['Wh'], w['dE1'], N, H_VP, 2 * L_VP, 2 * L_VP, H_VP, H_VP, gate=w['E1'], ldg=H_VP,
+                     gate_slope=0.01)
+                gemm(w['dE1'], vp['W1'], w['d_aa'].view(-1)[3:], N, 63, H_VP, H_VP, 63, 72, accumulate=True)
+            if full and w_vp:
+                lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, C.W2, None, 0, None, 0, None, None, w['signs'],
+                             w_vp / (N * NV * 3.0), w['dPO'], w['dA'], N)
+                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, w['dA'], None, w['dR_o'], w['dJ'].zero_(), N)
+                gemm(w['dPO'], C.PD, w['dR_o'].view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
+                     accumulate=True)
+                if self.compute_betas_grad:
+                    self._betas_grad(w, N, first=not need_2d)
+                lib.rodrigues_bwd(w['aa'].view(-1)[3:], 72, w['dR_o'].view(-1)[9:], 216, w['d_aa'].view(-1)[3:], 72,
+                                  23, 1, N * 23, 0)
+                dR[:, 0].add_(w['dR_o'][:, 0])
+            # axis-angle outputs of the pose head -> rotation matrices -> 6D -> MLP output
+            lib.rotmat2aa_bwd(w['R'], 9, w['d_aa'], 3, dR, 9, 1, 1, N * 24, 1)
+            w['dY'].zero_()
+            lib.rot6d_bwd(w['Y'], 147, dR, 216, w['dY'], 147, 24, 0, N * 24)
+            if need_2d:
+                w['dY'][:N, 144:147].copy_(w['dtr'])
+                w['dY'][N, 144:147].copy_(w['dtr'].sum(0).neg_())
+            self._motion_backward(w, N, vi)
+            if w_inst:
+                self.g_inst.gviews['learned_instance_code'].add_(
+                    self.g_inst.views['learned_instance_code'], alpha=2.0 * w_inst / (self.V * self.Cc))
+        elif need_2d:
+            lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox, self.focal, cx,
+                            cy, 100.0, mode_id, red, w['view_acc'], 0.0, w['dj25'], None, acc[4:5], N, 25, self.V, self.F)
+        # ---------------------------------------------------------------- losses -> one packed vector
+        norm = np.asarray([1.0 / (N * NV * 3.0), 1.0 / N, 1.0, 1.0 / N, 1.0, 1.0, 0.0, 0.0])
+        wkey = (w_vp, w_kl, w_3d, w_gmm, need_2d, w_inst)
+        cache = w.setdefault('wts_cache', {})
+        if wkey not in cache:
+            wt = np.asarray([w_vp, w_kl, w_3d, w_gmm, 1.0 if need_2d else 0.0, w_inst, 0.0, 0.0]) * norm
+            cache[wkey] = torch.tensor(wt, dtype=torch.float32, device=self.dev)
+        lib.combine_losses(acc, cache[wkey], 8, w['total'])
+        return w, norm
+
+    def _betas_grad(self, w, N, first):
+        """d learned_betas: the reference accumulates it on every backward although no optimiser owns it."""
+        C = self.C_
+        lib.colsum(w['dPO'], w['dbase'], N, 3 * VP, 3 * VP, 0)
+        gemm(w['dbase'], C.Sp, self.betas_grad, 1, 10, 3 * VP, 3 * VP, 3 * VP, 10, transB=True, accumulate=True)
+        gemm(w['dJ'], C.JSt, self.betas_grad, 1, 10, 72, 72, 72, 10, transB=True, accumulate=True)
+
+    def _motion_backward(self, w, N, vi):
+        mv, gv = self.g_motion.views, self.g_motion.gviews
+        Np, h, ind = N + 1, self.h, self.in_dim
+        W = lambda i: mv['learned_motion.net.net.%d.weight' % i]
+        gW = lambda i: gv['learned_motion.net.net.%d.weight' % i]
+        gb = lambda i: gv['learned_motion.net.net.%d.bias' % i]
+        dY = w['dY']
+        gemm(dY, w['H3'], self.gWhead, 147, h, Np, 147, h, h, transA=True)
+        lib.colsum(dY, self.gbhead, Np, 147, 147, 0)
+        gemm(dY, self.Whead, w['dHa'], Np, h, 147, 147, h, h, gate=w['H3'], ldg=h)
+        gemm(w['dHa'], w['H2'], gW(4), h, h, Np, h, h, h, transA=True)
+        lib.colsum(w['dHa'], gb(4), Np, h, h, 0)
+        gemm(w['dHa'], W(4), w['dHb'], Np, h, h, h, h, h, gate=w['H2'], ldg=h)
+        gemm(w['dHb'], w['H1'], gW(2), h, h, Np, h, h, h, transA=True)
+        lib.colsum(w['dHb'], gb(2), Np, h, h, 0)
+        gemm(w['dHb'], W(2), w['dHa'], Np, h, h, h, h, h, gate=w['H1'], ldg=h)
+        gemm(w['dHa'], w['X'], gW(0), h, ind, Np, h, ind, ind, transA=True)
+        lib.colsum(w['dHa'], gb(0), Np, h, h, 0)
+        gemm(w['dHa'], W(0), w['dX'], Np, ind, h, h, ind, ind)
+        gp, gg = self.g_phase.views, self.g_phase.gviews
+        lib.embed_bwd(w['raw'], vi, gp['shifts'], gp['scales'], self.K, self.centres,
+                      mv['phase_rbf.log_sigmas'] if self.D > 0 else None, self.D, self.basis, self.Cc, w['warped'],
+                      w['yn'], w['dX'], ind, gv['phase_rbf.log_sigmas'] if self.D > 0 else None, gg['shifts'],
+                      gg['scales'], self.g_inst.gviews['learned_instance_code'] if self.g_inst else None, w['gy01'], N,
+                      self.V)
+
+    def optimizer_step(self, which=None):
+        for g in (which or self.groups()):
+            g.adam_step()
+
+    # ------------------------------------------------------------------ read-backs
+    def loss_dict(self, w, norm):
+        """One packed device->host copy of the step's scalars (the reference does 5-7, :3564-3584)."""
+        host = torch.cat([w['acc'], w['total']]).cpu().numpy().astype(np.float64)
+        n = norm
+        d = dict(kp_loss=host[4], vp_recon_loss=host[0] * n[0], vp_kl_loss=host[1] * n[1], gmm_loss=host[3] * n[3],
+                 loss_3d=host[2], instance_loss=host[5], total_loss=host[8])
+        return {k: np.asarray(v, dtype=np.float32) for k, v in d.items()}
+
+    @torch.no_grad()
+    def predict(self, view_idx, frame_idx, add_trans=True, phases=None, want_vertices=True):
+        """get_preds_batch forward (:3637-3672): vertices (N,6890,3), the 25 loss joints, poses, orient, trans."""
+        C = self.C_
+        N = int(view_idx.shape[0])
+        w = self.ws(N)
+        w['vi'].copy_(view_idx)
+        if phases is None:
+            w['fi'].copy_(frame_idx)
+            torch.index_select(self.phase_table, 0, w['fi'], out=w['raw'])
+        else:
+            w['raw'].copy_(phases)
+        use_noise = self.version >= 3 and self.training and self.args.code_noise > 0 and self.Cc > 0
+        self._motion_forward(w, N, w['vi'], w['raw'], use_noise)
+        self._shape(w)
+        self._lbs_forward(w, N, w['R'], w['PO_m'], w['A_m'], w['JP'])
+        ro = self.ro
+        V = torch.empty(N, NV, 3, device=self.dev) if want_vertices else None
+        lib.skin_fwd(w['A_m'], w['PO_m'], w['base'], C.Wt, ro['Jx'] if ro['nx'] else None, ro['nx'],
+                     ro['slot'] if ro['np'] else None, ro['np'], V, w['JX'], N)
+        j = torch.empty(N, 25, 3, device=self.dev)
+        lib.joints_gather_fwd(w['JP'], w['JX'], ro['np'] + ro['nx'], ro['np'], self.map25, 25,
+                              w['trans'] if add_trans else None, None, j, N)
+        if want_vertices and add_trans:
+            V += w['trans'][:, None]
+        return dict(v=V, j=j, poses=w['aa'][:, 3:].clone(), orient=w['Y'][:N, :6].clone(),
+                    orient_aa=w['aa'][:, :3].clone(), trans=w['trans'].clone())

@@ -1,0 +1,465 @@
+"""torch.autograd.Function wrappers over the C ABI (include/nemo_b200.h).
+
+Every op runs a hand-written sm_100a kernel forward AND backward; there is no PyTorch/CPU
+fallback (a CPU tensor raises).  The reference functions each op stands in for are cited per class
+(paths under /root/reference).  PyTorch is used for memory, streams and autograd bookkeeping only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import assets
+from ._lib import lib, require_cuda
+
+VP = 6912
+NV = 6890
+ACT = {None: 0, 'none': 0, 'relu': 1, 'leaky_relu': 2}
+RBF_BASES = ['gaussian', 'linear', 'quadratic', 'inverse_quadratic', 'multiquadric', 'inverse_multiquadric',
+             'spline', 'poisson_one', 'poisson_two', 'matern32', 'matern52']
+KP_LOSSES = ['rmse', 'rmse_resized', 'mse', 'rmse_robust', 'mse_robust', 'mse_robust_resized']
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError('nemo_b200 ops are fp32 (like the reference); got %s' % t.dtype)
+    return t.contiguous()
+
+
+def _new(shape, like, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def gemm(A, B, C, M, N, K, lda, ldb, ldc, transA=False, transB=False, bias=None, act=0, gate=None, ldg=0,
+         gate_slope=0.0, accumulate=False):
+    """Raw C-ABI GEMM on device pointers/tensors (see nemo_b200_gemm)."""
+    lib.gemm(A, B, bias, C, M, N, K, lda, ldb, ldc, int(transA), int(transB), act, gate, ldg, float(gate_slope),
+             int(accumulate))
+
+
+# ----------------------------------------------------------------------------- rotations
+class _Rot6d(torch.autograd.Function):
+    """hmr.geometry.rot6d_to_rotmat (hmr/geometry.py:47-61)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x.reshape(-1, 6))
+        R = _new((x.shape[0], 3, 3), x)
+        lib.rot6d_fwd(x, 6, R, 9, 1, x.shape[0])
+        ctx.save_for_backward(x)
+        return R
+
+    @staticmethod
+    def backward(ctx, dR):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        lib.rot6d_bwd(x, 6, _f32c(dR), 9, dx, 6, 1, 0, x.shape[0])
+        return dx
+
+
+def rot6d_to_rotmat(x):
+    require_cuda()
+    shp = x.shape
+    R = _Rot6d.apply(x)
+    return R if x.dim() <= 2 and shp[-1] == 6 else R
+
+
+class _Rotmat2AA(torch.autograd.Function):
+    """hmr.geometry.rotation_matrix_to_angle_axis (hmr/geometry.py:181-346; nan_to_zero) and
+    human_body_prior.tools.rotation_tools.matrot2aa (tgm_conversion.py:219-376)."""
+
+    @staticmethod
+    def forward(ctx, R, nan_to_zero):
+        R = _f32c(R.reshape(-1, 3, 3))
+        aa = _new((R.shape[0], 3), R)
+        lib.rotmat2aa_fwd(R, 9, aa, 3, 1, R.shape[0], int(nan_to_zero))
+        ctx.save_for_backward(R)
+        ctx.nz = int(nan_to_zero)
+        return aa
+
+    @staticmethod
+    def backward(ctx, daa):
+        (R,) = ctx.saved_tensors
+        dR = torch.empty_like(R)
+        lib.rotmat2aa_bwd(R, 9, _f32c(daa), 3, dR, 9, 1, 0, R.shape[0], ctx.nz)
+        return dR, None
+
+
+def rotmat_to_aa(R, nan_to_zero=True):
+    require_cuda()
+    return _Rotmat2AA.apply(R, nan_to_zero)
+
+
+class _Rodrigues(torch.autograd.Function):
+    """kind 0: hmr.geometry.batch_rodrigues (hmr/geometry.py:9-45);
+    kind 1: human_body_prior.body_model.lbs.batch_rodrigues (lbs.py:303-334)."""
+
+    @staticmethod
+    def forward(ctx, aa, kind):
+        aa = _f32c(aa.reshape(-1, 3))
+        R = _new((aa.shape[0], 3, 3), aa)
+        lib.rodrigues_fwd(aa, 3, R, 9, 1, aa.shape[0], kind)
+        ctx.save_for_backward(aa)
+        ctx.kind = kind
+        return R
+
+    @staticmethod
+    def backward(ctx, dR):
+        (aa,) = ctx.saved_tensors
+        d = torch.empty_like(aa)
+        lib.rodrigues_bwd(aa, 3, _f32c(dR), 9, d, 3, 1, 0, aa.shape[0], ctx.kind)
+        return d, None
+
+
+def batch_rodrigues(aa, kind=0):
+    require_cuda()
+    return _Rodrigues.apply(aa, kind)
+
+
+# ----------------------------------------------------------------------------- projection
+class _Project(torch.autograd.Function):
+    """perspective_projection: hmr/geometry.py:78-106 (eps 0), utils/geometry.py:63-93 (eps 1e-8)."""
+
+    @staticmethod
+    def forward(ctx, points, rot, trans, focal, centre, eps):
+        B, P = points.shape[:2]
+        points, rot, trans = _f32c(points), _f32c(rot.reshape(B, 9)), _f32c(trans)
+        focal = _f32c(torch.as_tensor(focal, dtype=torch.float32, device=points.device).reshape(-1).expand(B))
+        centre = _f32c(centre.expand(B, 2))
+        out = _new((B, P, 2), points)
+        lib.project_fwd(points, rot, trans, focal, centre, float(eps), out, B, P)
+        ctx.save_for_backward(points, rot, trans, focal)
+        ctx.eps = float(eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        points, rot, trans, focal = ctx.saved_tensors
+        B, P = points.shape[:2]
+        dp, dr, dt = torch.empty_like(points), torch.empty_like(rot), torch.empty_like(trans)
+        lib.project_bwd(points, rot, trans, focal, ctx.eps, _f32c(dout), dp, dr, dt, B, P)
+        return dp, dr.view(B, 3, 3), dt, None, None, None
+
+
+def perspective_projection(points, rotation, translation, focal_length, camera_center, epsilon=0.0):
+    require_cuda()
+    return _Project.apply(points, rotation, translation, focal_length, camera_center, epsilon)
+
+
+# ----------------------------------------------------------------------------- linear layers
+class _Linear(torch.autograd.Function):
+    """y = act(x W^T + b): nn.Linear (+ReLU / LeakyReLU(0.01)) of FCNN/MotionNet
+    (nemo/neural_motion_model.py:58-71,130-148) and VPoser (vposer_model.py:63-88)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        x, W = _f32c(x), _f32c(W)
+        M, K = x.shape
+        N = W.shape[0]
+        y = _new((M, N), x)
+        gemm(x, W, y, M, N, K, K, K, N, transB=True, bias=None if b is None else _f32c(b), act=act)
+        ctx.save_for_backward(x, W, y)
+        ctx.act, ctx.has_b = act, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        M, K = x.shape
+        N = W.shape[0]
+        dy = _f32c(dy)
+        if ctx.act:
+            g = torch.empty_like(dy)
+            lib.act_bwd(dy, y, g, dy.numel(), ctx.act)
+            dy = g
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _new((M, K), x)
+            gemm(dy, W, dx, M, K, N, N, K, K)
+        if ctx.needs_input_grad[1]:
+            dW = _new((N, K), x)
+            gemm(dy, x, dW, N, K, M, N, K, K, transA=True)
+        if ctx.has_b and ctx.needs_input_grad[2]:
+            db = _new((N,), x)
+            lib.colsum(dy, db, M, N, N, 0)
+        return dx, dW, db, None
+
+
+def linear(x, W, b=None, act=None):
+    require_cuda()
+    return _Linear.apply(x, W, b, ACT[act] if not isinstance(act, int) else act)
+
+
+# ----------------------------------------------------------------------------- RBF / phase warp
+class _RBF(torch.autograd.Function):
+    """nemo.rbf.RBF.forward (nemo/rbf.py:47-56) with the 11 bases of :62-118."""
+
+    @staticmethod
+    def forward(ctx, x, centres, log_sigmas, basis):
+        x, centres, log_sigmas = _f32c(x.reshape(-1)), _f32c(centres.reshape(-1)), _f32c(log_sigmas)
+        N, D = x.shape[0], log_sigmas.shape[0]
+        out = _new((N, D), x)
+        lib.rbf_fwd(x, centres, log_sigmas, D, basis, out, N)
+        ctx.save_for_backward(x, centres, log_sigmas)
+        ctx.basis = basis
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, centres, log_sigmas = ctx.saved_tensors
+        N, D = x.shape[0], log_sigmas.shape[0]
+        dx = torch.empty_like(x)
+        dls = torch.zeros_like(log_sigmas)
+        lib.rbf_bwd(x, centres, log_sigmas, D, ctx.basis, _f32c(dout), dx, dls, N)
+        return dx.view(N, 1), None, dls, None
+
+
+def rbf(x, centres, log_sigmas, basis):
+    require_cuda()
+    return _RBF.apply(x, centres, log_sigmas, RBF_BASES.index(basis) if isinstance(basis, str) else basis)
+
+
+class _Monotonic(torch.autograd.Function):
+    """monotonic_network.MonotonicNetwork.forward (monotonic_network.py:23-39)."""
+
+    @staticmethod
+    def forward(ctx, x, shifts, scales):
+        x, shifts, scales = _f32c(x.reshape(-1)), _f32c(shifts), _f32c(scales)
+        out = torch.empty_like(x)
+        lib.monotonic_fwd(x, shifts, scales, shifts.shape[0], out, x.shape[0])
+        ctx.save_for_backward(x, shifts, scales)
+        return out.view(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, shifts, scales = ctx.saved_tensors
+        dx, dsh, dsc = torch.empty_like(x), torch.zeros_like(shifts), torch.zeros_like(scales)
+        scratch = _new((2,), x)
+        lib.monotonic_bwd(x, shifts, scales, shifts.shape[0], _f32c(dout.reshape(-1)), dx, dsh, dsc, scratch,
+                          x.shape[0])
+        return dx.view(-1, 1), dsh, dsc
+
+
+def monotonic(x, shifts, scales):
+    require_cuda()
+    return _Monotonic.apply(x, shifts, scales)
+
+
+# ----------------------------------------------------------------------------- GMM prior
+class _GMM(torch.autograd.Function):
+    """hmr.smplify.prior.MaxMixturePrior.merged_log_likelihood (hmr/smplify/prior.py:181-196)."""
+
+    @staticmethod
+    def forward(ctx, pose, means, precisions, nll_weights):
+        pose = _f32c(pose)
+        N, D = pose.shape
+        M = means.shape[0]
+        ll = _new((N,), pose)
+        g = _new((N, D), pose)
+        lib.gmm_prior(pose, D, _f32c(means), _f32c(precisions), _f32c(nll_weights.reshape(-1)), M, D, ll, 1.0, g, D,
+                      0, N)
+        ctx.save_for_backward(g)
+        return ll
+
+    @staticmethod
+    def backward(ctx, dll):
+        (g,) = ctx.saved_tensors
+        return g * dll[:, None], None, None, None
+
+
+def gmm_prior(pose, means, precisions, nll_weights):
+    require_cuda()
+    return _GMM.apply(pose, means, precisions, nll_weights)
+
+
+# ----------------------------------------------------------------------------- SMPL constants + LBS
+class SMPLConstants:
+    """Device-resident, kernel-ready SMPL data (HBM layout):
+
+      vt      (3,VP)      v_template, planar, zero padded
+      Sp      (10,3VP)    shapedirs as rows of the planar layout
+      PD      (207,3VP)   posedirs with columns permuted interleaved(v,c) -> planar(c,v)
+      basis   (217,3VP)   [PD; Sp] for per-frame betas
+      Jt      (72,)       J_regressor . v_template        JSt (10,72)  J_regressor . shapedirs (transposed)
+      Wt      (24,VP)     lbs_weights^T                   W2  (VP,8,4) the same, 3 joints per float4
+      Jx      (9,VP)      J_regressor_extra               rowsum (9,)
+      slot    int8 (VP,)  index into the 21 VertexJointSelector picks or -1
+    """
+
+    def __init__(self, sm: dict, device='cuda'):
+        require_cuda()
+        dev = torch.device(device)
+        f = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32)
+        vt = f(sm['v_template'])
+        sd = f(sm['shapedirs'])
+        pd = f(sm['posedirs'])
+        jr = f(sm['J_regressor'])
+        w = f(sm['lbs_weights'])
+        jx = f(sm['J_regressor_extra'])
+        self.num_betas = sd.shape[2]
+
+        def planar(rows):  # (R, 6890, 3) -> (R, 3*VP)
+            out = torch.zeros(rows.shape[0], 3, VP)
+            out[:, :, :NV] = rows.permute(0, 2, 1)
+            return out.reshape(rows.shape[0], 3 * VP)
+
+        self.vt = planar(vt[None])[0].view(3, VP).to(dev).contiguous()
+        self.Sp = planar(sd.permute(2, 0, 1)).to(dev).contiguous()
+        self.PD = planar(pd.view(207, NV, 3)).to(dev).contiguous()
+        self.basis = torch.cat([self.PD, self.Sp], 0).contiguous()
+        self.Jt = (jr.double() @ vt.double()).float().reshape(72).to(dev)
+        self.JSt = torch.einsum('jv,vcl->ljc', jr.double(), sd.double()).float().reshape(self.num_betas, 72).to(dev).contiguous()
+        wt = torch.zeros(24, VP)
+        wt[:, :NV] = w.t()
+        self.Wt = wt.to(dev).contiguous()
+        w2 = torch.zeros(VP, 8, 4)
+        w2[:NV, :, :3] = w.view(NV, 8, 3)
+        self.W2 = w2.to(dev).contiguous()
+        self.set_readouts(np.asarray(sm['vertex_joint_ids']), jx)
+        self.parents = torch.as_tensor(np.asarray(sm['parents']), dtype=torch.int32).to(dev)
+        self.joint_map = torch.as_tensor(np.asarray(sm['joint_map']), dtype=torch.int32).to(dev)
+        self.faces = np.asarray(sm['faces'])
+        self.device = dev
+        # fp32 originals for the API-facing buffers of the module mirrors
+        self.raw = {k: f(sm[k]).to(dev) for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor',
+                                                   'lbs_weights', 'J_regressor_extra')}
+
+    def make_readout(self, pick_ids, jx_rows):
+        """(slot int8 (VP,), np, Jx (nx,VP), nx, rowsum (nx,)) for a set of vertex picks / regressor rows."""
+        pick_ids = np.asarray(pick_ids, dtype=np.int64).reshape(-1)
+        if len(set(pick_ids.tolist())) != len(pick_ids):
+            raise ValueError('vertex pick ids must be unique')
+        slot = -np.ones(VP, np.int8)
+        slot[pick_ids] = np.arange(len(pick_ids), dtype=np.int8)
+        jx_rows = torch.as_tensor(jx_rows, dtype=torch.float32).reshape(-1, NV)
+        jxp = torch.zeros(jx_rows.shape[0], VP)
+        jxp[:, :NV] = jx_rows.cpu()
+        dev = self.vt.device
+        return dict(slot=torch.from_numpy(slot).to(dev), np=len(pick_ids), Jx=jxp.to(dev).contiguous(),
+                    nx=jx_rows.shape[0], rowsum=jx_rows.double().sum(1).float().to(dev))
+
+    def set_readouts(self, pick_ids, jx_rows):
+        self.readout = self.make_readout(pick_ids, jx_rows)
+
+
+class _LBS(torch.autograd.Function):
+    """lbs (human_body_prior/body_model/lbs.py:164-254) on rotation matrices + the joint read-outs of
+    smplx VertexJointSelector / hmr.smpl.SMPL (hmr/smpl.py:33-36).
+
+    rot (N,24,3,3); betas (1,nb) shared or (N,nb) per frame.
+    returns vertices (N,6890,3) [or None], posed joints JP (N,24,3), read-outs JX (N,np+nx,3)."""
+
+    @staticmethod
+    def forward(ctx, rot, betas, C, readout, want_vertices):
+        N = rot.shape[0]
+        rot = _f32c(rot.reshape(N, 24, 9))
+        betas = _f32c(betas)
+        per_frame = betas.shape[0] != 1
+        nb = betas.shape[1]
+        dev = rot.device
+        if per_frame:
+            if betas.shape[0] != N:
+                raise ValueError('betas batch %d does not match pose batch %d' % (betas.shape[0], N))
+            K = 207 + nb
+            F = _new((N, K), rot)
+            F[:, 207:] = betas
+            basis, base = C.basis, C.vt
+            J = _new((N, 72), rot)
+            gemm(betas, C.JSt, J, N, 72, nb, nb, 72, 72, bias=C.Jt)
+            js = 72
+        else:
+            K = 207
+            F = _new((N, K), rot)
+            basis = C.PD
+            base = _new((3, VP), rot)
+            gemm(betas, C.Sp, base, 1, 3 * VP, nb, nb, 3 * VP, 3 * VP, bias=C.vt.view(-1))
+            J = _new((72,), rot)
+            gemm(betas, C.JSt, J, 1, 72, nb, nb, 72, 72, bias=C.Jt)
+            js = 0
+        lib.pose_feature(rot, F, K, N)
+        PO = _new((N, 3 * VP), rot)
+        gemm(F, basis, PO, N, 3 * VP, K, K, 3 * VP, 3 * VP)
+        A = _new((N, 24, 12), rot)
+        JP = _new((N, 24, 3), rot)
+        lib.chain_fwd(rot, J, js, C.parents, A, JP, N)
+        ro = readout
+        V = _new((N, NV, 3), rot) if want_vertices else None
+        JX = _new((N, ro['np'] + ro['nx'], 3), rot)
+        lib.skin_fwd(A, PO, base, C.Wt, ro['Jx'] if ro['nx'] else None, ro['nx'],
+                     ro['slot'] if ro['np'] else None, ro['np'], V, JX if JX.numel() else None, N)
+        ctx.save_for_backward(rot, betas, F, PO, base, J, A)
+        ctx.C, ctx.ro, ctx.per_frame, ctx.js = C, ro, per_frame, js
+        if V is None:
+            V = torch.empty(0, device=dev)
+        return V, JP, JX
+
+    @staticmethod
+    def backward(ctx, dV, dJP, dJX):
+        rot, betas, F, PO, base, J, A = ctx.saved_tensors
+        C, ro = ctx.C, ctx.ro
+        N, K, nb = rot.shape[0], F.shape[1], betas.shape[1]
+        dV = None if dV is None or dV.numel() == 0 else _f32c(dV)
+        dJX = None if dJX is None or dJX.numel() == 0 else _f32c(dJX)
+        dJP = None if dJP is None else _f32c(dJP)
+        dPO = _new((N, 3 * VP), rot)
+        dA = _new((N, 24, 12), rot)
+        lib.skin_bwd(A, PO, base, C.Wt, C.W2, ro['Jx'] if ro['nx'] else None, ro['nx'],
+                     ro['slot'] if ro['np'] else None, ro['np'], dV, dJX, None, 0.0, dPO, dA, N)
+        dR = _new((N, 24, 9), rot)
+        dJ = _new((N, 72), rot) if ctx.per_frame else torch.zeros(72, device=rot.device)
+        lib.chain_bwd(rot, J, ctx.js, C.parents, dA, dJP, dR, dJ, N)
+        dbetas = None
+        need_b = ctx.needs_input_grad[1]
+        # dR[:, 1:] += dPO . PD^T, written in place through the leading dimension (pose_feature backward)
+        gemm(dPO, C.PD, dR.view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True, accumulate=True)
+        if ctx.per_frame:
+            if need_b:
+                dbetas = _new((N, nb), rot)
+                gemm(dPO, C.Sp, dbetas, N, nb, 3 * VP, 3 * VP, 3 * VP, nb, transB=True)
+                gemm(dJ, C.JSt, dbetas, N, nb, 72, 72, 72, nb, transB=True, accumulate=True)
+        else:
+            if need_b:
+                dbase = _new((3 * VP,), rot)
+                lib.colsum(dPO, dbase, N, 3 * VP, 3 * VP, 0)
+                dbetas = _new((1, nb), rot)
+                gemm(dbase, C.Sp, dbetas, 1, nb, 3 * VP, 3 * VP, 3 * VP, nb, transB=True)
+                gemm(dJ, C.JSt, dbetas, 1, nb, 72, 72, 72, nb, transB=True, accumulate=True)
+        return dR.view(N, 24, 3, 3), dbetas, None, None, None
+
+
+def lbs_rotmats(rot, betas, C: SMPLConstants, readout=None, want_vertices=True):
+    require_cuda()
+    V, JP, JX = _LBS.apply(rot, betas, C, readout or C.readout, want_vertices)
+    return (V if want_vertices else None), JP, JX
+
+
+class _JointsGather(torch.autograd.Function):
+    """joints = cat(JP, JX)[:, joint_map] (+ transl): smplx SMPL.forward + hmr/smpl.py:33-37."""
+
+    @staticmethod
+    def forward(ctx, JP, JX, jmap, np_, transl, rowsum):
+        N = JP.shape[0]
+        JP, JX = _f32c(JP), _f32c(JX)
+        nout = jmap.shape[0]
+        out = _new((N, nout, 3), JP)
+        tr = None if transl is None else _f32c(transl)
+        lib.joints_gather_fwd(JP, JX if JX.numel() else None, JX.shape[1], np_, jmap, nout, tr, rowsum, out, N)
+        ctx.meta = (JX.shape[1], np_, nout, transl is not None)
+        ctx.save_for_backward(jmap, rowsum if rowsum is not None else torch.empty(0, device=JP.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        jmap, rowsum = ctx.saved_tensors
+        nx_raw, np_, nout, has_t = ctx.meta
+        N = dout.shape[0]
+        dout = _f32c(dout)
+        dJP, dJX = _new((N, 24, 3), dout), _new((N, nx_raw, 3), dout)
+        dtr = _new((N, 3), dout) if has_t else None
+        lib.joints_gather_bwd(dout, nx_raw, np_, jmap, nout, rowsum if rowsum.numel() else None, dJP,
+                              dJX if nx_raw else None, dtr, N)
+        return dJP, dJX, None, None, dtr, None
+
+
+def joints_gather(JP, JX, jmap, np_, transl=None, rowsum=None):
+    return _JointsGather.apply(JP, JX, jmap, np_, transl, rowsum)

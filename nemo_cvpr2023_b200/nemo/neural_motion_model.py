@@ -1,0 +1,481 @@
+"""Mirror of the fit models of `nemo/neural_motion_model.py`: FCNN (:58), RotNet (:74), MotionNet (:106),
+MultiViewModel (:151) and NemoV1..V4 (:3364, :3675, :3786, :3959) with the reference's method names,
+arguments, return values and state_dict keys.  `step`, `warmup`, `opt_cam`, `get_preds_batch`,
+`get_preds` run on the fused engine (fit_engine.FitEngine): hand-written CUDA forward + backward +
+Adam, no autograd graph.  Rendering / offline evaluation methods (:282-2756) are out of scope."""
+from collections import defaultdict
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import assets
+from .. import functional as Fn
+from ..fit_engine import FitEngine
+from ..hmr.smpl import SMPL
+from ..hmr.smplify.prior import MaxMixturePrior
+from ..human_body_prior.models.vposer_model import VPoser
+from ..monotonic_network import MonotonicNetwork
+from .rbf import RBF
+from .utils import GMoF, ravel_first_2dims
+
+MAX_SIZE = 2000
+
+
+class _ViewLinear(nn.Module):
+    """nn.Linear whose parameters are views into the engine's flat buffers."""
+
+    def __init__(self, weight, bias):
+        super().__init__()
+        self.weight, self.bias = nn.Parameter(weight), nn.Parameter(bias)
+        self.in_features, self.out_features = weight.shape[1], weight.shape[0]
+
+    def forward(self, x, act=None):
+        return Fn.linear(x, self.weight, self.bias, act)
+
+
+class FCNN(nn.Module):
+    """:58-71.  `net` keeps the Sequential indices 0/2/4 of the reference for state_dict parity."""
+
+    def __init__(self, input_dim=None, h_dim=None, output_dim=None, _views=None, device='cuda'):
+        super().__init__()
+        if _views is None:
+            mk = lambda o, i: (torch.empty(o, i, device=device).uniform_(-1, 1) / i ** 0.5,
+                               torch.empty(o, device=device).uniform_(-1, 1) / i ** 0.5)
+            _views = [mk(h_dim, input_dim), mk(h_dim, h_dim), mk(output_dim, h_dim)]
+        self.net = nn.ModuleDict({'0': _ViewLinear(*_views[0]), '2': _ViewLinear(*_views[1]),
+                                  '4': _ViewLinear(*_views[2])})
+
+    def forward(self, x, last_act=None):
+        x = self.net['0'](x, 'relu')
+        x = self.net['2'](x, 'relu')
+        return self.net['4'](x, last_act)
+
+
+def _head_init(n_joints, fcnn_dim, device, init_last_layer_zero):
+    w = torch.empty(n_joints * 6, fcnn_dim, device=device)
+    nn.init.xavier_uniform_(w, gain=0.00001 if init_last_layer_zero else 0.01)
+    if init_last_layer_zero:
+        b = torch.tensor([1, 0, 0, 1, 0, 0], device=device).float().repeat(n_joints)
+    else:
+        b = torch.empty(n_joints * 6, device=device).uniform_(-1, 1) / fcnn_dim ** 0.5
+    return w, b
+
+
+class RotNet(nn.Module):
+    """:74-103 (NemoV0 only)."""
+
+    def __init__(self, input_dim, fcnn_dim, n_joints, init_last_layer_zero=False, device='cuda'):
+        super().__init__()
+        self.n_joints = n_joints
+        self.net = FCNN(input_dim, fcnn_dim, fcnn_dim, device=device)
+        self.linear = _ViewLinear(*_head_init(n_joints, fcnn_dim, device, init_last_layer_zero))
+
+    def forward(self, x):
+        z = self.net(x, 'relu')
+        rot6d = self.linear(z)
+        rotmat = Fn.rot6d_to_rotmat(rot6d.reshape(-1, 6)).view(x.shape[0], self.n_joints, 3, 3)
+        pose = Fn.rotmat_to_aa(rotmat.reshape(-1, 3, 3), True).reshape(-1, 3 * self.n_joints)
+        return {'rot6d': rot6d, 'rotmat': rotmat, 'pose': pose}
+
+
+class MotionNet(nn.Module):
+    """:106-148.  Stand-alone use goes through the autograd ops; inside the fit models the same
+    parameters are driven by the fused engine."""
+
+    def __init__(self, input_dim=None, fcnn_dim=None, n_joints=24, n_linear_out=3, init_last_layer_zero=False,
+                 _views=None, device='cuda'):
+        super().__init__()
+        self.n_joints = n_joints
+        if _views is None:
+            self.net = FCNN(input_dim, fcnn_dim, fcnn_dim, device=device)
+            self.rot_out = _ViewLinear(*_head_init(n_joints, fcnn_dim, device, init_last_layer_zero))
+            self.linear_out = _ViewLinear(torch.empty(n_linear_out, fcnn_dim, device=device).uniform_(-1, 1) / fcnn_dim ** 0.5,
+                                          torch.empty(n_linear_out, device=device).uniform_(-1, 1) / fcnn_dim ** 0.5)
+        else:
+            g = lambda k: _views['learned_motion.' + k]
+            self.net = FCNN(_views=[(g('net.net.%d.weight' % i), g('net.net.%d.bias' % i)) for i in (0, 2, 4)])
+            self.rot_out = _ViewLinear(g('rot_out.weight'), g('rot_out.bias'))
+            self.linear_out = _ViewLinear(g('linear_out.weight'), g('linear_out.bias'))
+
+    def forward(self, x):
+        B = x.shape[0]
+        z = self.net(x, 'relu')
+        rot6d = self.rot_out(z)
+        rotmat = Fn.rot6d_to_rotmat(rot6d.reshape(-1, 6)).view(B, self.n_joints, 3, 3)
+        pose = Fn.rotmat_to_aa(rotmat.reshape(-1, 3, 3), True).reshape(-1, 3 * self.n_joints)
+        trans = self.linear_out(z)
+        orient_dict = {'rot6d': rot6d[:, :6], 'rotmat': rotmat[:, :1], 'pose': pose[:, :3]}
+        pose_dict = {'rot6d': rot6d[:, 6:], 'rotmat': rotmat[:, 1:], 'pose': pose[:, 3:]}
+        return pose_dict, orient_dict, trans
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam/AdamW-compatible handle (param_groups, state_dict, zero_grad, step) on one flat
+    engine buffer; `step()` is one launch of nemo_b200_adam."""
+
+    def __init__(self, params, group, lr, weight_decay=0.0, decoupled=False):
+        self._g = group
+        super().__init__(list(params), dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay,
+                                            decoupled=decoupled))
+
+    def zero_grad(self, set_to_none=False):
+        self._g.g.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        pg = self.param_groups[0]
+        self._g.lr, self._g.wd, self._g.betas, self._g.eps = pg['lr'], pg['weight_decay'], pg['betas'], pg['eps']
+        self._g.adam_step()
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd['flat'] = dict(m=self._g.m.clone(), v=self._g.v.clone(), step=self._g.step_dev.clone())
+        return sd
+
+    def load_state_dict(self, sd):
+        flat = sd.get('flat')
+        if flat is not None:
+            self._g.m.copy_(flat['m'])
+            self._g.v.copy_(flat['v'])
+            self._g.step_dev.copy_(flat['step'])
+        else:  # a checkpoint written by the reference (torch.optim.Adam): per-parameter state
+            o = 0
+            for i, p in enumerate(self.param_groups[0]['params']):
+                st = sd['state'].get(i)
+                k = p.numel()
+                if st is not None:
+                    self._g.m[o:o + k].copy_(st['exp_avg'].reshape(-1))
+                    self._g.v[o:o + k].copy_(st['exp_avg_sq'].reshape(-1))
+                    self._g.step_dev.fill_(int(st['step']))
+                o += k
+        for k in ('lr', 'weight_decay'):
+            if sd.get('param_groups'):
+                self.param_groups[0][k] = sd['param_groups'][0][k]
+
+
+class MultiViewModel(nn.Module):
+    """:151-255 + the fit-path methods (:2758-3124).  Extra keyword arguments replace the licensed files the
+    reference loads from `software/`: `smpl_arrays`, `vposer_state`, `gmm` (default: seeded synthetic
+    stand-ins of the exact shapes, see assets.py)."""
+
+    VERSION = 1
+
+    def __init__(self, args, multi_view_seqs, device='cuda', smpl_arrays=None, vposer_state=None, gmm=None,
+                 init_params=None):
+        super().__init__()
+        self.args = args
+        if not hasattr(self.args, 'include_vs'):
+            self.args.include_vs = False
+            self.args.include_pare = False
+        self.FOCAL_LENGTH = assets.FOCAL_LENGTH
+        self.IMG_D0, self.IMG_D1 = multi_view_seqs.IMG_D0, multi_view_seqs.IMG_D1
+        self.n_joints = 23
+        self.device = device
+        self.multi_view_seqs = multi_view_seqs
+        self.num_views, self.num_frames = multi_view_seqs.num_views, multi_view_seqs.num_frames
+        self.smpl = SMPL(smpl_arrays if smpl_arrays is not None else 'synthetic', batch_size=1, create_transl=False,
+                         device=device)
+        self.criterion_keypoints = nn.MSELoss(reduction='none')
+        self.robustifier = GMoF()
+        vposer_state = vposer_state if vposer_state is not None else assets.make_vposer_weights(2)
+        self.vp = VPoser(state_dict=vposer_state, device=device)
+        self.l1_loss = nn.L1Loss(reduction='mean')
+        gmm = gmm if gmm is not None else assets.make_gmm(3)
+        self.pose_prior = MaxMixturePrior(num_gaussians=8, gmm=gmm, device=device)
+        self.points2d_gt_all, self.gt_bbox_size = self.collate_gt_2d()
+        hmr = np.stack([np.asarray(multi_view_seqs.sequences[v]['pose']) for v in range(self.num_views)])
+        self.hmr_theta = torch.tensor(hmr[:, :, 3:-1], dtype=torch.float32, device=device)
+        self.hmr_mask = torch.tensor(hmr[:, :, -1:], dtype=torch.float32, device=device)
+        data = dict(points2d_gt_all=self.points2d_gt_all.cpu().numpy(), gt_bbox_size=self.gt_bbox_size.cpu().numpy(),
+                    hmr_theta=hmr[:, :, 3:-1], hmr_mask=hmr[:, :, -1:], IMG_D0=self.IMG_D0, IMG_D1=self.IMG_D1)
+        if init_params is None:
+            init_params = self._reference_init()
+        self.engine = FitEngine(self.args, self.num_views, self.num_frames, self.smpl.consts, vposer_state, gmm, data,
+                                version=self.VERSION, device=device, init_params=init_params)
+        self._bind_parameters()
+        self.training = False
+
+    # ---- construction helpers
+    def _reference_init(self):
+        """Initial values as NemoV1/V2.__init__ draws them (:3375-3402, :3685-3692)."""
+        a = self.args
+        rbf_dim = a.phase_rbf_dim if self.VERSION >= 2 else 0
+        shadow = deepcopy(a)
+        shadow.phase_rbf_dim = rbf_dim
+        p = assets.make_fit_params(shadow, self.num_views, seed=int(torch.randint(0, 2 ** 31 - 1, (1,))),
+                                   img_d0=self.IMG_D0, rot_out_std=0.0)
+        w = torch.empty(144, a.h_dim)
+        nn.init.xavier_uniform_(w, gain=0.00001)
+        p['learned_motion.rot_out.weight'] = w.numpy()
+        return p
+
+    def _bind_parameters(self):
+        e = self.engine
+        P = nn.Parameter
+        self.learned_cameras = P(e.g_cam.views['learned_cameras'])
+        if e.g_inst is not None:
+            self.learned_instance_code = P(e.g_inst.views['learned_instance_code'])
+        self.learned_motion = MotionNet(_views=e.g_motion.views)
+        self.learned_betas = P(e.betas)
+        nets = []
+        for v in range(self.num_views):
+            m = MonotonicNetwork.__new__(MonotonicNetwork)
+            nn.Module.__init__(m)
+            m.n_nodes = e.K
+            m.shifts, m.scales = P(e.g_phase.views['shifts'][v]), P(e.g_phase.views['scales'][v])
+            nets.append(m)
+        self.phase_networks = nn.ModuleList(nets)
+        if e.D > 0:
+            rbf = RBF.__new__(RBF)
+            nn.Module.__init__(rbf)
+            rbf.in_features, rbf.out_features, rbf.basis_name = 1, e.D, self.args.rbf_kernel
+            rbf.register_buffer('centres', e.centres.view(-1, 1))
+            rbf.log_sigmas = P(e.g_motion.views['phase_rbf.log_sigmas'])
+            self.phase_rbf = rbf
+        # .grad of every parameter aliases the engine's flat gradient buffers
+        grads = e.named_grads()
+        for k, p in self.named_parameters():
+            if k in grads:
+                p.grad = grads[k]
+        a = self.args
+        self.opt_cameras = FusedAdam([self.learned_cameras], e.g_cam, a.lr_camera)
+        motion = list(self.learned_motion.parameters()) + (list(self.phase_rbf.parameters()) if e.D > 0 else [])
+        self.opt_motion = FusedAdam(motion, e.g_motion, a.lr_human, a.wd_human, decoupled=(a.opt_human == 'adamw'))
+        self.opt_phase = FusedAdam(self.phase_networks.parameters(), e.g_phase, a.lr_phase)
+        self.optimizers = [self.opt_cameras, self.opt_motion, self.opt_phase]
+        if e.g_inst is not None:
+            self.opt_instance = FusedAdam([self.learned_instance_code], e.g_inst, a.lr_instance)
+            self.optimizers.append(self.opt_instance)
+        if a.lr_factor < 1:
+            self.schedulers = [torch.optim.lr_scheduler.ReduceLROnPlateau(o, factor=a.lr_factor, min_lr=1e-6)
+                               for o in self.optimizers]
+
+    def _apply(self, fn, recurse=True):
+        # parameters are views into the engine's flat CUDA buffers: moving the module would detach them
+        return self
+
+    # ---- data
+    def collate_gt_2d(self, label_type=None):
+        """:2908-2961"""
+        label_type = label_type or self.args.label_type
+        key = {'op': 'pose_2d_op', 'gt': 'pose_2d_gt', 'vibe': 'vibe_joints2d', 'pare': 'pare_joints2d',
+               'vs': 'vs_joints2d'}
+        gt = []
+        for v in range(self.num_views):
+            seq = self.multi_view_seqs.sequences[v]
+            if label_type == 'intersection':
+                g1, g2 = np.array(seq['pose_2d_op']), np.array(seq['pose_2d_gt'])
+                mean = (g1 + g2)[..., :2] / 2
+                dist = np.sqrt(np.power(g1[..., :2] - g2[..., :2], 2).sum(-1, keepdims=True))
+                conf = (dist < self.args.label_intersection_threshold).astype('float32') * g1[..., -1:]
+                gt.append(np.concatenate([mean, conf], -1))
+            else:
+                gt.append(seq[key[label_type]])
+        pts = torch.tensor(np.array(gt)).float().to(self.device)
+        d0 = pts[..., 0].max(-1)[0] - pts[..., 0].min(-1)[0]
+        d1 = pts[..., 1].max(-1)[0] - pts[..., 1].min(-1)[0]
+        return pts, torch.sqrt(d0 ** 2 + d1 ** 2) + 1e-4
+
+    # ---- checkpointing (:257-280)
+    def save(self, path):
+        torch.save({'model_sd': self.state_dict(), 'opt_sd': [o.state_dict() for o in self.optimizers]}, path)
+
+    def load(self, path):
+        saved = torch.load(path, weights_only=False)
+        sd = {k: v for k, v in saved['model_sd'].items()
+              if not any(k.startswith(m) for m in ('vp', 'pose_prior', 'renderer', 'smpl'))}
+        self.load_state_dict(sd, strict=False)
+        for i, opt in enumerate(self.optimizers):
+            opt.load_state_dict(saved['opt_sd'][i])
+
+    # ---- forward API
+    def frame_idx_to_raw_phase(self, frame_idx):
+        """:2978-2984"""
+        return self.engine.phase_table[frame_idx.to(self.engine.dev)]
+
+    def _idx(self, t):
+        return torch.as_tensor(t).long()
+
+    def get_preds_batch(self, view_idx, frame_idx, add_trans=True, phases=None, detach_pose=False):
+        """:3637-3672 / :3968-4008.  Tensors are results of the fused forward (no autograd graph)."""
+        self.engine.training = self.training
+        out = self.engine.predict(self._idx(view_idx), None if frame_idx is None else self._idx(frame_idx),
+                                  add_trans=add_trans, phases=phases)
+        out['view_idx'], out['frame_idx'] = view_idx, frame_idx
+        return out
+
+    def get_preds(self, add_trans=True):
+        """:2986-3003: one get_preds_batch per view, stacked to (V, F, ...)."""
+        all_preds = defaultdict(list)
+        for i in range(self.num_views):
+            vi = i * torch.ones(self.num_frames).long().to(self.device)
+            fi = torch.arange(self.num_frames).long().to(self.device)
+            for k, v in self.get_preds_batch(vi, fi, add_trans=add_trans).items():
+                all_preds[k].append(v)
+        return {k: torch.stack(v) for k, v in all_preds.items()}
+
+    def _get_smpl_given_poses(self, pose_input, orient, pose_type):
+        """:2963-2976"""
+        if pose_type == 'aa':
+            rot = Fn.batch_rodrigues(pose_input.reshape(-1, 3), kind=0).reshape(-1, 23, 3, 3)
+        elif pose_type == 'rotmat':
+            rot = pose_input
+        return self.smpl(betas=self.learned_betas, body_pose=rot,
+                         global_orient=Fn.rot6d_to_rotmat(orient).unsqueeze(1), pose2rot=False)
+
+    def learned_camera_projection(self, input_points3d, view_idx):
+        """:3073-3124, batched: the camera of each sample is looked up by view_idx."""
+        cam = self.learned_cameras[view_idx.to(self.learned_cameras.device).long()]
+        rot = Fn.rot6d_to_rotmat(cam[:, 3:].contiguous())
+        n = input_points3d.shape[0]
+        dev = input_points3d.device
+        centre = torch.tensor([[float(self.IMG_D0 // 2), float(self.IMG_D1 // 2)]], device=dev).expand(n, 2)
+        return Fn.perspective_projection(input_points3d, rot, cam[:, :3].contiguous(),
+                                         torch.full((n,), self.FOCAL_LENGTH, device=dev), centre, 0.0)
+
+    def keypoint_loss(self, pred_keypoints_2d, gt_keypoints_2d, gt_weight, gt_size=None, loss_type=None):
+        """:2806-2843 (API form; inside step() the same arithmetic is fused into the projection kernel)."""
+        loss_type = loss_type or self.args.loss
+        m = (gt_weight > 0.5).float()
+        if loss_type in ('rmse', 'rmse_resized'):
+            if loss_type == 'rmse_resized':
+                s = gt_size.unsqueeze(-1).unsqueeze(-1)
+                pred_keypoints_2d, gt_keypoints_2d = pred_keypoints_2d / s, gt_keypoints_2d / s
+            return m * torch.sqrt(1e-6 + self.criterion_keypoints(pred_keypoints_2d, gt_keypoints_2d).sum(-1, keepdim=True))
+        if loss_type == 'mse':
+            return m * self.criterion_keypoints(pred_keypoints_2d, gt_keypoints_2d)
+        if loss_type == 'rmse_robust':
+            return m * self.robustifier(pred_keypoints_2d - gt_keypoints_2d, sqrt=True)
+        if loss_type == 'mse_robust':
+            return m * self.robustifier(pred_keypoints_2d - gt_keypoints_2d, sqrt=False)
+        if loss_type == 'mse_robust_resized':
+            s = gt_size.unsqueeze(-1).unsqueeze(-1)
+            return m * self.robustifier(pred_keypoints_2d / s * 1000 - gt_keypoints_2d / s * 1000, sqrt=False)
+        raise ValueError(loss_type)
+
+    def gmm_prior_loss(self, poses, orient_aa, betas):
+        """:2758-2773"""
+        return self.pose_prior(poses, betas).mean()
+
+    def vposer_loss(self, poses, orient):
+        """:2775-2804 (API form on the autograd ops)."""
+        N = poses.size(0)
+        q_z = self.vp.encode(poses[:, :63].contiguous())
+        dec = self.vp.decode(q_z.mean)['pose_body'].contiguous().view(N, -1)
+        recon = torch.cat([dec, poses[:, 63:]], 1)
+        bm_orig = self._get_smpl_given_poses(poses, orient, 'aa')
+        bm_rec = self._get_smpl_given_poses(recon.contiguous().view(N, -1), orient, 'aa')
+        v2v = self.l1_loss(bm_rec.vertices.detach(), bm_orig.vertices)
+        p_z = torch.distributions.normal.Normal(torch.zeros_like(q_z.mean), torch.ones_like(q_z.mean))
+        kl = torch.mean(torch.sum(torch.distributions.kl.kl_divergence(q_z, p_z), dim=[1]))
+        return v2v, kl
+
+    # ---- optimisation
+    _LOSS_KEYS = ['kp_loss', 'gmm_loss', 'vp_recon_loss', 'vp_kl_loss', 'total_loss']
+
+    def _full_indices(self):
+        v = torch.arange(self.num_views).repeat_interleave(self.num_frames)
+        f = torch.arange(self.num_frames).repeat(self.num_views)
+        return v, f
+
+    def step(self, view_idx, frame_idx, update=True, full_batch=False):
+        """:3511-3598 / :3796-3909 -> (loss_dict of numpy scalars, info_dict)."""
+        e = self.engine
+        if update and self.VERSION >= 3:
+            self.training = True
+        e.training = self.training
+        if not (self.args.batch_size > -1 and not full_batch):
+            view_idx, frame_idx = self._full_indices()
+        vi, fi = self._idx(view_idx), self._idx(frame_idx)
+        w, norm = e.forward_backward(vi, fi, update=update, mode='step')
+        if update:
+            for opt in self.optimizers:
+                opt.step()
+        ld = e.loss_dict(w, norm)
+        loss_dict = {k: ld[k] for k in self._LOSS_KEYS}
+        if update and self.args.lr_factor < 1:
+            for s in self.schedulers:
+                s.step(float(ld['total_loss']))
+        info_dict = {'view_idx': w['vi'].clone(), 'frame_idx': w['fi'].clone(), 'loss_all': w['loss_all'].clone(),
+                     'points2d_gt': self.points2d_gt_all[w['vi'], w['fi']]}
+        self.training = False
+        return loss_dict, info_dict
+
+    def _sample(self):
+        bs = self.args.batch_size
+        return torch.randint(0, self.num_views, size=(bs,)), torch.randint(0, self.num_frames, size=(bs,))
+
+    def warmup(self, warmup_steps=1000):
+        """:3455-3509: fit the predicted axis-angle poses to the VIBE thetas (GMoF), stepping the motion
+        and phase optimisers only.  (The reference also runs the unused LBS here; it is skipped.)"""
+        if warmup_steps == 0:
+            return []
+        if not self.args.batch_size > -1:
+            raise NotImplementedError()
+        e = self.engine
+        losses = []
+        for _ in range(warmup_steps):
+            vi, fi = self._sample()
+            w, _ = e.forward_backward(vi, fi, update=True, mode='warmup')
+            self.opt_motion.step()
+            self.opt_phase.step()
+            losses.append(w['acc'][2])
+        return [float(x) for x in torch.stack(losses).cpu()]
+
+    def opt_cam(self, cam_opt_steps=2000):
+        """:2869-2906: Adam on the cameras only, first frame of every view, plain-mean reprojection loss."""
+        e = self.engine
+        vi, fi = torch.arange(self.num_views), torch.zeros(self.num_views, dtype=torch.long)
+        e.g_cam.m.zero_(), e.g_cam.v.zero_(), e.g_cam.step_dev.zero_()   # the reference builds a fresh Adam here
+        e.g_cam.lr = self.args.lr_camera
+        log = []
+        for _ in range(cam_opt_steps):
+            w, _ = e.forward_backward(vi, fi, update=True, mode='cam_fit')
+            e.g_cam.adam_step()
+            log.append(w['acc'][4].clone())
+        return [np.asarray(x) for x in torch.stack(log).cpu().numpy()] if log else []
+
+
+class NemoV1(MultiViewModel):
+    """:3364-3672: a single network for pose + orient + trans."""
+    VERSION = 1
+
+
+class NemoV2(NemoV1):
+    """:3675-3781: V1 + RBF phase features."""
+    VERSION = 2
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.detach_articulation = False
+        self.start_global_traj_anywhere = False
+
+
+class NemoV3(NemoV2):
+    """:3786-3956: V2 + instance-code regulariser + 3D pose loss (+ optional code noise while training)."""
+    VERSION = 3
+    _LOSS_KEYS = ['kp_loss', 'gmm_loss', 'vp_recon_loss', 'instance_loss', 'loss_3d', 'vp_kl_loss', 'total_loss']
+
+
+class NemoV4(NemoV3):
+    """:3959-4149: V3 with OP-Nose as joint 0 and the batch opt_cam that steps every optimiser."""
+    VERSION = 4
+
+    def opt_cam(self, cam_opt_steps=2000):
+        if not self.args.batch_size > -1:
+            raise NotImplementedError()
+        e = self.engine
+        for _ in range(cam_opt_steps):
+            vi, fi = self._sample()
+            e.forward_backward(vi, fi, update=True, mode='opt_cam', detach_pose=True)
+            for opt in self.optimizers:
+                opt.step()
+
+
+class NemoV0(MultiViewModel):
+    """:3127-3361 (separate RotNet / FCNN per quantity).  Not run by any shipped script; not built."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError('NemoV0 is outside the accelerated path; use NemoV1..V4')
