@@ -126,15 +126,15 @@ int gemm_simt(const float* A, const float* B, const float* bias, float* C, int M
 extern "C" int nemo_b200_gemm_simt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
                                    int lda, int ldb, int ldc, int transA, int transB, int act, const float* gate,
                                    int ldg, float gate_slope, int accumulate, void* stream) {
-  NB_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0 && act >= 0 && act <= 2, "gemm: bad args");
   if (M == 0 || N == 0) return 0;
+  NB_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0 && act >= 0 && act <= 2, "gemm: bad args");
   return nb::gemm_simt(A, B, bias, C, M, N, K, lda, ldb, ldc, transA, transB, act, gate, ldg, gate_slope, accumulate,
                        S(stream));
 }
 
 extern "C" int nemo_b200_colsum(const float* X, float* out, int M, int N, int ld, int accumulate, void* stream) {
-  NB_REQUIRE(X && out && M >= 0 && N >= 0 && ld >= N, "colsum: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(X && out && M >= 0 && N >= 0 && ld >= N, "colsum: bad args");
   if (!accumulate) NB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, S(stream)));
   if (M == 0) return 0;
   int rows = 256;

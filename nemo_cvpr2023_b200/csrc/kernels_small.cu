@@ -104,49 +104,49 @@ __global__ void k_pose_feature(const float* __restrict__ R, float* __restrict__ 
 #define NB_ROT_ARGS_OK (B >= 0 && per_row >= 1)
 
 extern "C" int nemo_b200_rot6d_fwd(const float* x6, int ld6, float* R, int ldr, int per_row, int B, void* stream) {
-  NB_REQUIRE(x6 && R && NB_ROT_ARGS_OK, "rot6d_fwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(x6 && R && NB_ROT_ARGS_OK, "rot6d_fwd: bad args");
   k_rot6d_fwd<<<NB_1D(B)>>>(x6, ld6, R, ldr, per_row, B);
   NB_LAUNCH_CHECK("rot6d_fwd");
 }
 extern "C" int nemo_b200_rot6d_bwd(const float* x6, int ld6, const float* dR, int ldr, float* dx6, int ldd,
                                    int per_row, int accumulate, int B, void* stream) {
-  NB_REQUIRE(x6 && dR && dx6 && NB_ROT_ARGS_OK, "rot6d_bwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(x6 && dR && dx6 && NB_ROT_ARGS_OK, "rot6d_bwd: bad args");
   k_rot6d_bwd<<<NB_1D(B)>>>(x6, ld6, dR, ldr, dx6, ldd, per_row, accumulate, B);
   NB_LAUNCH_CHECK("rot6d_bwd");
 }
 extern "C" int nemo_b200_rotmat2aa_fwd(const float* R, int ldr, float* aa, int lda, int per_row, int B,
                                        int nan_to_zero, void* stream) {
-  NB_REQUIRE(R && aa && NB_ROT_ARGS_OK, "rotmat2aa_fwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(R && aa && NB_ROT_ARGS_OK, "rotmat2aa_fwd: bad args");
   k_r2aa_fwd<<<NB_1D(B)>>>(R, ldr, aa, lda, per_row, B, nan_to_zero);
   NB_LAUNCH_CHECK("rotmat2aa_fwd");
 }
 extern "C" int nemo_b200_rotmat2aa_bwd(const float* R, int ldr, const float* daa, int lda, float* dR, int ldd,
                                        int per_row, int accumulate, int B, int nan_to_zero, void* stream) {
-  NB_REQUIRE(R && daa && dR && NB_ROT_ARGS_OK, "rotmat2aa_bwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(R && daa && dR && NB_ROT_ARGS_OK, "rotmat2aa_bwd: bad args");
   k_r2aa_bwd<<<NB_1D(B)>>>(R, ldr, daa, lda, dR, ldd, per_row, accumulate, B, nan_to_zero);
   NB_LAUNCH_CHECK("rotmat2aa_bwd");
 }
 extern "C" int nemo_b200_rodrigues_fwd(const float* aa, int lda, float* R, int ldr, int per_row, int B, int kind,
                                        void* stream) {
-  NB_REQUIRE(aa && R && NB_ROT_ARGS_OK && (kind == 0 || kind == 1), "rodrigues_fwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(aa && R && NB_ROT_ARGS_OK && (kind == 0 || kind == 1), "rodrigues_fwd: bad args");
   k_rod_fwd<<<NB_1D(B)>>>(aa, lda, R, ldr, per_row, B, kind);
   NB_LAUNCH_CHECK("rodrigues_fwd");
 }
 extern "C" int nemo_b200_rodrigues_bwd(const float* aa, int lda, const float* dR, int ldr, float* daa, int ldd,
                                        int per_row, int accumulate, int B, int kind, void* stream) {
-  NB_REQUIRE(aa && dR && daa && NB_ROT_ARGS_OK && (kind == 0 || kind == 1), "rodrigues_bwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(aa && dR && daa && NB_ROT_ARGS_OK && (kind == 0 || kind == 1), "rodrigues_bwd: bad args");
   k_rod_bwd<<<NB_1D(B)>>>(aa, lda, dR, ldr, daa, ldd, per_row, accumulate, B, kind);
   NB_LAUNCH_CHECK("rodrigues_bwd");
 }
 extern "C" int nemo_b200_pose_feature(const float* R, float* F, int ldf, int N, void* stream) {
-  NB_REQUIRE(R && F && N >= 0 && ldf >= 207, "pose_feature: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(R && F && N >= 0 && ldf >= 207, "pose_feature: bad args");
   k_pose_feature<<<NB_1D((long long)N * 207)>>>(R, F, ldf, N);
   NB_LAUNCH_CHECK("pose_feature");
 }
@@ -197,15 +197,15 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
 }
 extern "C" int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride, const int* parents, float* A,
                                    float* JP, int N, void* stream) {
-  NB_REQUIRE(R && J && parents && A && JP && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_fwd: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(R && J && parents && A && JP && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_fwd: bad args");
   k_chain_fwd<<<cdiv(N, 64), 64, 0, S(stream)>>>(R, J, j_stride, parents, A, JP, N);
   NB_LAUNCH_CHECK("chain_fwd");
 }
 extern "C" int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents, const float* dA,
                                    const float* dJP, float* dR, float* dJ, int N, void* stream) {
-  NB_REQUIRE(R && J && parents && dR && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_bwd: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(R && J && parents && dR && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_bwd: bad args");
   k_chain_bwd<<<cdiv(N, 64), 64, 0, S(stream)>>>(R, J, j_stride, parents, dA, dJP, dR, dJ, N);
   NB_LAUNCH_CHECK("chain_bwd");
 }
@@ -255,17 +255,17 @@ __global__ void k_jgather_bwd(const float* __restrict__ dout, int nx_raw, int np
 extern "C" int nemo_b200_joints_gather_fwd(const float* JP, const float* JX, int nraw_x, int np, const int* joint_map,
                                            int nout, const float* transl, const float* rowsum, float* out, int N,
                                            void* stream) {
+  if (N == 0) return 0;
   NB_REQUIRE(JP && joint_map && out && N >= 0 && nout > 0 && nraw_x >= 0 && np >= 0 && np <= nraw_x &&
                  (nraw_x == 0 || JX), "joints_gather_fwd: bad args");
-  if (N == 0) return 0;
   k_jgather_fwd<<<NB_1D((long long)N * nout * 3)>>>(JP, JX, nraw_x, np, joint_map, nout, transl, rowsum, out, N);
   NB_LAUNCH_CHECK("joints_gather_fwd");
 }
 extern "C" int nemo_b200_joints_gather_bwd(const float* dout, int nraw_x, int np, const int* joint_map, int nout,
                                            const float* rowsum, float* dJP, float* dJX, float* dtransl, int N,
                                            void* stream) {
-  NB_REQUIRE(dout && joint_map && dJP && N >= 0 && nout > 0 && (nraw_x == 0 || dJX), "joints_gather_bwd: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(dout && joint_map && dJP && N >= 0 && nout > 0 && (nraw_x == 0 || dJX), "joints_gather_bwd: bad args");
   k_jgather_bwd<<<NB_1D((long long)N * (NJ + nraw_x + 1) * 3)>>>(dout, nraw_x, np, joint_map, nout, rowsum, dJP, dJX,
                                                                  dtransl, N);
   NB_LAUNCH_CHECK("joints_gather_bwd");
@@ -323,16 +323,16 @@ __global__ void k_project_bwd(const float* __restrict__ pts, const float* __rest
 }
 extern "C" int nemo_b200_project_fwd(const float* points, const float* rot, const float* trans, const float* focal,
                                      const float* centre, float eps, float* out, int B, int P, void* stream) {
-  NB_REQUIRE(points && rot && trans && focal && centre && out && B >= 0 && P > 0, "project_fwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(points && rot && trans && focal && centre && out && B >= 0 && P > 0, "project_fwd: bad args");
   k_project_fwd<<<NB_1D((long long)B * P)>>>(points, rot, trans, focal, centre, eps, out, B, P);
   NB_LAUNCH_CHECK("project_fwd");
 }
 extern "C" int nemo_b200_project_bwd(const float* points, const float* rot, const float* trans, const float* focal,
                                      float eps, const float* dout, float* dpoints, float* drot, float* dtrans, int B,
                                      int P, void* stream) {
-  NB_REQUIRE(points && rot && trans && focal && dout && B >= 0 && P > 0, "project_bwd: bad args");
   if (B == 0) return 0;
+  NB_REQUIRE(points && rot && trans && focal && dout && B >= 0 && P > 0, "project_bwd: bad args");
   k_project_bwd<<<NB_1D(B)>>>(points, rot, trans, focal, eps, dout, dpoints, drot, dtrans, B, P);
   NB_LAUNCH_CHECK("project_bwd");
 }
@@ -447,10 +447,10 @@ extern "C" int nemo_b200_kp_loss_fwd(const float* joints, const int64_t* view_id
                                      const float* cameras, const float* gt, const float* bbox, float focal, float cx,
                                      float cy, float rho, int loss_type, int reduction, float* points2d,
                                      float* loss_all, float* view_acc, int N, int P, int V, int F, void* stream) {
+  if (N == 0) return 0;
   NB_REQUIRE(joints && view_idx && frame_idx && cameras && gt && view_acc && N >= 0 && P > 0 && V > 0 && F > 0 &&
                  loss_type >= 0 && loss_type <= 5, "kp_loss_fwd: bad args");
   NB_REQUIRE(!(loss_type == 1 || loss_type == 5) || bbox, "kp_loss_fwd: resized loss needs bbox");
-  if (N == 0) return 0;
   k_kp_fwd<<<NB_1D(N)>>>(joints, view_idx, frame_idx, cameras, gt, bbox, focal, cx, cy, rho, loss_type, reduction,
                          points2d, loss_all, view_acc, N, P, V, F);
   NB_LAUNCH_CHECK("kp_loss_fwd");
@@ -460,9 +460,9 @@ extern "C" int nemo_b200_kp_loss_bwd(const float* joints, const int64_t* view_id
                                      float cy, float rho, int loss_type, int reduction, const float* view_acc,
                                      float weight, float* djoints, float* dcam_acc, float* loss_out, int N, int P,
                                      int V, int F, void* stream) {
+  if (N == 0) return 0;
   NB_REQUIRE(joints && view_idx && frame_idx && cameras && gt && view_acc && djoints && N >= 0 && P > 0 && V > 0 &&
                  F > 0 && loss_type >= 0 && loss_type <= 5, "kp_loss_bwd: bad args");
-  if (N == 0) return 0;
   k_kp_bwd<<<NB_1D(N)>>>(joints, view_idx, frame_idx, cameras, gt, bbox, focal, cx, cy, rho, loss_type, reduction,
                          view_acc, weight, djoints, dcam_acc, loss_out, N, P, V, F);
   NB_LAUNCH_CHECK("kp_loss_bwd");
@@ -503,9 +503,9 @@ __global__ void k_pose3d(const float* __restrict__ pose, int ldp, const int64_t*
 extern "C" int nemo_b200_pose3d_loss(const float* pose, int ldp, const int64_t* view_idx, const int64_t* frame_idx,
                                      const float* target, const float* mask, float rho, float weight, float* loss_acc,
                                      float* dpose, int ldd, int accumulate, int N, int D, int F, void* stream) {
+  if (N == 0) return 0;
   NB_REQUIRE(pose && view_idx && frame_idx && target && mask && N >= 0 && D > 0 && F > 0 && ldp >= D,
              "pose3d_loss: bad args");
-  if (N == 0) return 0;
   k_pose3d<<<NB_1D((long long)N * D)>>>(pose, ldp, view_idx, frame_idx, target, mask, rho, weight, loss_acc, dpose,
                                         ldd, accumulate, N, D, F);
   NB_LAUNCH_CHECK("pose3d_loss");
@@ -725,22 +725,22 @@ __global__ void k_mono_bwd(const float* __restrict__ x, const float* __restrict_
 }
 extern "C" int nemo_b200_rbf_fwd(const float* x, const float* centres, const float* log_sigmas, int D, int basis,
                                  float* out, int N, void* stream) {
-  NB_REQUIRE(x && centres && log_sigmas && out && D > 0 && N >= 0 && basis >= 0 && basis <= 10, "rbf_fwd: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(x && centres && log_sigmas && out && D > 0 && N >= 0 && basis >= 0 && basis <= 10, "rbf_fwd: bad args");
   k_rbf_fwd<<<NB_1D((long long)N * D)>>>(x, centres, log_sigmas, D, basis, out, N);
   NB_LAUNCH_CHECK("rbf_fwd");
 }
 extern "C" int nemo_b200_rbf_bwd(const float* x, const float* centres, const float* log_sigmas, int D, int basis,
                                  const float* dout, float* dx, float* dlog_sigmas, int N, void* stream) {
-  NB_REQUIRE(x && centres && log_sigmas && dout && D > 0 && N >= 0 && basis >= 0 && basis <= 10, "rbf_bwd: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(x && centres && log_sigmas && dout && D > 0 && N >= 0 && basis >= 0 && basis <= 10, "rbf_bwd: bad args");
   k_rbf_bwd<<<cdiv(N, 4), 128, 0, S(stream)>>>(x, centres, log_sigmas, D, basis, dout, dx, dlog_sigmas, N);
   NB_LAUNCH_CHECK("rbf_bwd");
 }
 extern "C" int nemo_b200_monotonic_fwd(const float* x, const float* shifts, const float* scales, int K, float* out,
                                        int N, void* stream) {
-  NB_REQUIRE(x && shifts && scales && out && K > 0 && N >= 0, "monotonic_fwd: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(x && shifts && scales && out && K > 0 && N >= 0, "monotonic_fwd: bad args");
   k_mono_fwd<<<cdiv(N, 4), 128, 0, S(stream)>>>(x, shifts, scales, K, out, N);
   NB_LAUNCH_CHECK("monotonic_fwd");
 }
@@ -834,9 +834,9 @@ __global__ void __launch_bounds__(256) k_gmm(const float* __restrict__ pose, int
 extern "C" int nemo_b200_gmm_prior(const float* pose, int ldp, const float* means, const float* precisions,
                                    const float* nll_weights, int M, int D, float* ll, float gscale, float* dpose,
                                    int ldd, int accumulate, int N, void* stream) {
+  if (N == 0) return 0;
   NB_REQUIRE(pose && means && precisions && nll_weights && M > 0 && D == GD && ldp >= D && N >= 0,
              "gmm_prior: bad args (D must be 69)");
-  if (N == 0) return 0;
   k_gmm<<<cdiv(N, 32), 256, 0, S(stream)>>>(pose, ldp, means, precisions, nll_weights, M, ll, gscale, dpose, ldd,
                                             accumulate, N);
   NB_LAUNCH_CHECK("gmm_prior");
@@ -867,8 +867,8 @@ __global__ void k_vp_kl(const float* __restrict__ head, int L, float* __restrict
 }
 extern "C" int nemo_b200_vposer_kl(const float* head, int L, float* sigma, float* kl_acc, float gscale, float* dhead,
                                    int N, void* stream) {
-  NB_REQUIRE(head && L > 0 && N >= 0, "vposer_kl: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(head && L > 0 && N >= 0, "vposer_kl: bad args");
   k_vp_kl<<<NB_1D((long long)N * L)>>>(head, L, sigma, kl_acc, gscale, dhead, N);
   NB_LAUNCH_CHECK("vposer_kl");
 }
@@ -890,8 +890,8 @@ __global__ void k_increment(int* c) { *c += 1; }
 extern "C" int nemo_b200_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int decoupled, int step,
                               const int* step_dev, void* stream) {
-  NB_REQUIRE(p && g && m && v && (step >= 1 || step_dev), "adam: bad args");
   if (n == 0) return 0;
+  NB_REQUIRE(p && g && m && v && (step >= 1 || step_dev), "adam: bad args");
   float bc1 = 1.f - powf(beta1, (float)step);
   float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   k_adam<<<cdiv((long long)n, 256), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled,
@@ -908,8 +908,8 @@ __global__ void k_scale_add(float* __restrict__ y, const float* __restrict__ x, 
   if (i < n) y[i] += a * x[i];
 }
 extern "C" int nemo_b200_scale_add(float* y, const float* x, float a, size_t n, void* stream) {
-  NB_REQUIRE(y && x, "scale_add: bad args");
   if (n == 0) return 0;
+  NB_REQUIRE(y && x, "scale_add: bad args");
   k_scale_add<<<cdiv((long long)n, 256), 256, 0, S(stream)>>>(y, x, a, n);
   NB_LAUNCH_CHECK("scale_add");
 }
@@ -919,8 +919,8 @@ __global__ void k_act_bwd(const float* __restrict__ dy, const float* __restrict_
   if (i < n) out[i] = dy[i] * (y[i] > 0.f ? 1.f : slope);
 }
 extern "C" int nemo_b200_act_bwd(const float* dy, const float* y, float* out, size_t n, int act, void* stream) {
-  NB_REQUIRE(dy && y && out && (act == 1 || act == 2), "act_bwd: bad args");
   if (n == 0) return 0;
+  NB_REQUIRE(dy && y && out && (act == 1 || act == 2), "act_bwd: bad args");
   k_act_bwd<<<cdiv((long long)n, 256), 256, 0, S(stream)>>>(dy, y, out, n, act == 1 ? 0.f : 0.01f);
   NB_LAUNCH_CHECK("act_bwd");
 }

@@ -441,9 +441,9 @@ constexpr int L1_FB = 4;
 
 extern "C" int nemo_b200_skin_fwd(const float* A, const float* PO, const float* base, const float* Wt, const float* Jx,
                                   int nx, const signed char* slot, int np, float* V, float* JX, int N, void* stream) {
+  if (N == 0) return 0;
   NB_REQUIRE(A && base && Wt && N >= 0 && nx >= 0 && nx <= 10 && np >= 0 && np <= 22, "skin_fwd: bad args");
   NB_REQUIRE((nx == 0 || Jx) && (np == 0 || slot) && (nx + np == 0 || JX), "skin_fwd: joint read-out pointers missing");
-  if (N == 0) return 0;
   dim3 grid(cdiv(N, FWD_FB));
   cudaStream_t s = S(stream);
 #define NB_SKF(NXP, WV) k_skin_fwd<FWD_FB, NXP, WV><<<grid, SK_THREADS, 0, s>>>(A, PO, base, Wt, Jx, nx, np ? slot : nullptr, np, V, JX, N)
@@ -459,8 +459,8 @@ extern "C" int nemo_b200_skin_fwd(const float* A, const float* PO, const float* 
 extern "C" int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const float* A_b, const float* PO_b,
                                      const float* base, const float* Wt, uint32_t* signs, float* l1_sum, int N,
                                      void* stream) {
-  NB_REQUIRE(A_a && PO_a && A_b && PO_b && base && Wt && l1_sum && N >= 0, "skin_l1_fwd: bad args");
   if (N == 0) return 0;
+  NB_REQUIRE(A_a && PO_a && A_b && PO_b && base && Wt && l1_sum && N >= 0, "skin_l1_fwd: bad args");
   k_skin_l1_fwd<L1_FB><<<cdiv(N, L1_FB), SK_THREADS, 0, S(stream)>>>(A_a, PO_a, A_b, PO_b, base, Wt, signs, l1_sum, N);
   NB_LAUNCH_CHECK("skin_l1_fwd");
 }
@@ -469,10 +469,10 @@ extern "C" int nemo_b200_skin_bwd(const float* A, const float* PO, const float* 
                                   const float* Jx, int nx, const signed char* slot, int np, const float* dV,
                                   const float* dJX, const uint32_t* signs, float sign_scale, float* dPO, float* dA,
                                   int N, void* stream) {
+  if (N == 0) return 0;
   NB_REQUIRE(A && base && Wt && W2 && dA && N >= 0 && nx >= 0 && nx <= 10 && np >= 0 && np <= 22,
              "skin_bwd: bad args");
   NB_REQUIRE(!dJX || ((nx == 0 || Jx) && (np == 0 || slot)), "skin_bwd: joint read-out pointers missing");
-  if (N == 0) return 0;
   constexpr size_t smem = bwd_smem_bytes<BWD_FB>();
   static_assert(4 * BWD_FB * 288 <= SK_TILE * 32 + 2 * SK_TILE * SG_STRIDE, "reduction scratch too small");
   const int nxe = dJX ? nx : 0;

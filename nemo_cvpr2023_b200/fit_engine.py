@@ -406,6 +406,10 @@ class FitEngine:
         dY = w['dY']
         gemm(dY, w['H3'], self.gWhead, 147, h, Np, 147, h, h, transA=True)
         lib.colsum(dY, self.gbhead, Np, 147, 147, 0)
+        # d/d linear_out.bias of (trans - trans_0) cancels exactly (row N of dY is minus the column sum of the
+        # rows above it); keep it an exact 0 like the reference instead of summation-order noise that Adam
+        # would amplify into lr-sized steps
+        self.gbhead[144:147].zero_()
         gemm(dY, self.Whead, w['dHa'], Np, h, 147, 147, h, h, gate=w['H3'], ldg=h)
         gemm(w['dHa'], w['H2'], gW(4), h, h, Np, h, h, h, transA=True)
         lib.colsum(w['dHa'], gb(4), Np, h, h, 0)

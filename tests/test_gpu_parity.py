@@ -7,7 +7,7 @@ import torch
 from nemo_cvpr2023_b200 import assets
 from oracle import nemo_oracle as O
 from oracle.make_golden import VSUB, step_case
-from tests.util import (T, TOL_GRAD_REL, TOL_LOSS_REL, TOL_VERT_ABS, assert_abs, assert_grad, assert_rel, gold, npy)
+from tests.util import (assert_adam_param, T, TOL_GRAD_REL, TOL_LOSS_REL, TOL_VERT_ABS, assert_abs, assert_grad, assert_rel, gold, npy)
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -100,8 +100,8 @@ def test_gemm_matches_fp64(Fn, ta, tb):
         ref = np.where(ref > 0, ref, 0.01 * ref)
         C = torch.empty(M, N, device=DEV)
         Fn.gemm(G(A), G(B), C, M, N, K, A.shape[1], B.shape[1], N, bool(ta), bool(tb), bias=G(bias), act=2)
-        scale = np.sqrt(K)
-        assert_abs(npy(C), ref, 2e-6 * scale * 4, 'gemm %s' % ((M, N, K),))
+        # fp32 accumulation over K terms of magnitude ~1: a few ulp of the largest output
+        assert_abs(npy(C), ref, 2e-5 * np.abs(ref).max(), 'gemm %s' % ((M, N, K),))
 
 
 def test_lbs_axis_angle(Fn, smpl):
@@ -249,7 +249,7 @@ def test_step_matches_reference(version):
         for k, ref in g.items():
             pre = 's%d_param.' % s
             if k.startswith(pre):
-                assert_abs(npy(params[k[len(pre):]]), ref, 2e-5 * max(1.0, np.abs(ref).max()), k)
+                assert_adam_param(npy(params[k[len(pre):]]), ref, k)
     # state_dict carries the reference's key names
     sd = m.state_dict()
     for k in g:

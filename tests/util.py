@@ -37,7 +37,12 @@ def grad_err(g, ref):
     return l2, mx
 
 
-def assert_grad(g, ref, tol=TOL_GRAD_REL, what=''):
+def assert_grad(g, ref, tol=TOL_GRAD_REL, what='', zero_atol=1e-3):
+    if np.abs(np.asarray(ref)).max() == 0:
+        # exactly cancelling gradient in the reference (e.g. d/d linear_out.bias of trans - trans_0):
+        # relative error is undefined, only summation-order noise may remain
+        assert np.abs(np.asarray(g)).max() <= zero_atol, '%s: reference gradient is 0, got %.3e' % (what, np.abs(g).max())
+        return
     l2, mx = grad_err(g, ref)
     assert l2 <= tol and mx <= tol, '%s: grad rel-L2 %.3e, rel-max %.3e > %.1e' % (what, l2, mx, tol)
 
@@ -51,3 +56,15 @@ def assert_rel(a, ref, tol, what=''):
     a, ref = float(a), float(ref)
     assert abs(a - ref) <= tol * max(abs(ref), 1e-30), '%s: %r vs %r (rel %.3e > %.1e)' % (
         what, a, ref, abs(a - ref) / max(abs(ref), 1e-30), tol)
+
+
+def assert_adam_param(p, ref, what='', lr=1e-1):
+    """Parameters after Adam steps.  Adam moves every weight by ~lr * g/(|g| + eps): entries whose gradient is
+    summation-order noise around 0 can legitimately differ by a fraction of lr, so the bulk must agree
+    tightly (99.5% within 2e-5 of the value scale) and no entry may be off by more than one lr-sized step."""
+    p, ref = np.asarray(p, np.float64), np.asarray(ref, np.float64)
+    d = np.abs(p - ref)
+    scale = max(1.0, np.abs(ref).max())
+    frac = (d > 2e-5 * scale).mean()
+    assert frac <= 5e-3, '%s: %.3f%% of entries differ by more than 2e-5' % (what, 100 * frac)
+    assert d.max() <= 2.5 * lr, '%s: max abs err %.3e' % (what, d.max())
