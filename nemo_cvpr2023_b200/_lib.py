@@ -51,6 +51,16 @@ class _Lib:
         self._dll = None
         self.protos = parse_header()
         self.launches = 0   # kernels of this library launched so far (bench.py reports the delta)
+        self.profile = None  # set to {} to collect per-entry-point device time (CUDA events; tools/profile_step.py)
+        self._pending, self.tag = [], ''
+
+    def collect_profile(self):
+        torch.cuda.synchronize()
+        for name, e0, e1 in self._pending:
+            t, n = self.profile.get(name, (0.0, 0))
+            self.profile[name] = (t + e0.elapsed_time(e1), n + 1)
+        self._pending = []
+        return self.profile
 
     def load(self):
         if self._dll is None:
@@ -80,7 +90,14 @@ class _Lib:
             a = [_arg(x) for x in args]
             if has_stream:
                 a.append(torch.cuda.current_stream().cuda_stream)
-            rc = fn(*a)
+            if self.profile is not None and has_stream:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*a)
+                e1.record()
+                self._pending.append((short + (':' + self.tag if self.tag else ''), e0, e1))
+            else:
+                rc = fn(*a)
             if rc != 0:
                 raise RuntimeError('%s failed (%d): %s' % (name, rc, dll.nemo_b200_last_error().decode()))
         call.__name__ = name

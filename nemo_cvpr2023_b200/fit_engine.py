@@ -147,6 +147,13 @@ class FitEngine:
         self.map25 = torch.tensor(m25, dtype=torch.int32, device=self.dev)
         self._ws = {}
         self.training = False
+        self.world, self.loss_scale = 1, 1.0
+
+    def enable_data_parallel(self, world_size):
+        """Shard by video instance: this rank owns its views' cameras, instance codes and
+        phase networks; the shared motion MLP + RBF gradients are summed over ranks with one NCCL allreduce per
+        step.  The global loss is the mean of the ranks' losses, so local gradients are scaled by 1/world."""
+        self.world, self.loss_scale = int(world_size), 1.0 / int(world_size)
 
     # ------------------------------------------------------------------ parameters
     def named_params(self):
@@ -271,6 +278,7 @@ class FitEngine:
         mode_id = KP_LOSSES.index(a.loss)
         red = 1 if mode == 'cam_fit' else 0
         cx, cy = float(self.IMG_D0 // 2), float(self.IMG_D1 // 2)   # (:3104-3106) height/2 is used as cx
+        ls = self.loss_scale
         acc = w['acc']   # 0 l1_sum, 1 kl_sum, 2 loss_3d, 3 gmm_sum, 4 kp, 5 instance
         if need_2d:
             self._lbs_forward(w, N, w['R'], w['PO_m'], w['A_m'], w['JP'])
@@ -293,7 +301,7 @@ class FitEngine:
             # VPoser encode (mean) -> decode (:2779-2784)
             gemm(w['aa'].view(-1)[3:], vp['W1'], w['E1'], N, H_VP, 63, 72, 63, H_VP, transB=True, bias=vp['b1'], act=2)
             gemm(w['E1'], vp['Wh'], w['head'], N, 2 * L_VP, H_VP, H_VP, H_VP, 2 * L_VP, transB=True, bias=vp['bh'])
-            lib.vposer_kl(w['head'], L_VP, None, acc[1:2], w_kl / N, w['dhead'], N)
+            lib.vposer_kl(w['head'], L_VP, None, acc[1:2], ls * w_kl / N, w['dhead'], N)
             gemm(w['head'], vp['Wd0'], w['D1'], N, H_VP, L_VP, 2 * L_VP, L_VP, H_VP, transB=True, bias=vp['bd0'], act=2)
             gemm(w['D1'], vp['Wd3'], w['D2'], N, H_VP, H_VP, H_VP, H_VP, H_VP, transB=True, bias=vp['bd3'], act=2)
             gemm(w['D2'], vp['Wd5'], w['D3'], N, 126, H_VP, H_VP, H_VP, 126, transB=True, bias=vp['bd5'])
@@ -310,10 +318,10 @@ class FitEngine:
             lib.skin_l1_fwd(w['A_o'], w['PO_o'], w['A_r'], w['PO_r'], w['base'], C.Wt, w['signs'], acc[0:1], N)
             # GMM prior (:2758-2773): value and (scaled) gradient in one pass
             lib.gmm_prior(w['aa'].view(-1)[3:], 72, self.gmm_means, self.gmm_prec, self.gmm_w, self.gmm_means.shape[0],
-                          69, w['ll'], w_gmm / N, w['d_aa'].view(-1)[3:] if update else None, 72, 1, N)
+                          69, w['ll'], ls * w_gmm / N, w['d_aa'].view(-1)[3:] if update else None, 72, 1, N)
             lib.colsum(w['ll'], acc[3:4], N, 1, 1, 1)
         if w_3d or (self.version >= 3 and full and getattr(a, 'weight_3d_loss', 0.0)):
-            lib.pose3d_loss(w['aa'].view(-1)[3:], 72, vi, fi, self.hmr_theta, self.hmr_mask, 100.0, w_3d, acc[2:3],
+            lib.pose3d_loss(w['aa'].view(-1)[3:], 72, vi, fi, self.hmr_theta, self.hmr_mask, 100.0, ls * w_3d, acc[2:3],
                             w['d_aa'].view(-1)[3:] if update else None, 72, 1, N, 69, self.F)
         if w_inst:
             code = self.g_inst.views['learned_instance_code']
@@ -326,7 +334,7 @@ class FitEngine:
             dR = w['dR']
             if need_2d:
                 lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox,
-                                self.focal, cx, cy, 100.0, mode_id, red, w['view_acc'], 1.0, w['dj25'], w['dcam'].zero_(),
+                                self.focal, cx, cy, 100.0, mode_id, red, w['view_acc'], ls, w['dj25'], w['dcam'].zero_(),
                                 acc[4:5], N, 25, self.V, self.F)
                 lib.cam_finish(self.g_cam.views['learned_cameras'], w['dcam'], self.g_cam.gviews['learned_cameras'],
                                0, self.V)
@@ -357,7 +365,7 @@ class FitEngine:
                 gemm(w['dE1'], vp['W1'], w['d_aa'].view(-1)[3:], N, 63, H_VP, H_VP, 63, 72, accumulate=True)
             if full and w_vp:
                 lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, C.W2, None, 0, None, 0, None, None, w['signs'],
-                             w_vp / (N * NV * 3.0), w['dPO'], w['dA'], N)
+                             ls * w_vp / (N * NV * 3.0), w['dPO'], w['dA'], N)
                 lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, w['dA'], None, w['dR_o'], w['dJ'].zero_(), N)
                 gemm(w['dPO'], C.PD, w['dR_o'].view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
                      accumulate=True)
@@ -374,9 +382,11 @@ class FitEngine:
                 w['dY'][:N, 144:147].copy_(w['dtr'])
                 w['dY'][N, 144:147].copy_(w['dtr'].sum(0).neg_())
             self._motion_backward(w, N, vi)
+            if self.world > 1:
+                torch.distributed.all_reduce(self.g_motion.g)
             if w_inst:
                 self.g_inst.gviews['learned_instance_code'].add_(
-                    self.g_inst.views['learned_instance_code'], alpha=2.0 * w_inst / (self.V * self.Cc))
+                    self.g_inst.views['learned_instance_code'], alpha=ls * 2.0 * w_inst / (self.V * self.Cc))
         elif need_2d:
             lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox, self.focal, cx,
                             cy, 100.0, mode_id, red, w['view_acc'], 0.0, w['dj25'], None, acc[4:5], N, 25, self.V, self.F)
