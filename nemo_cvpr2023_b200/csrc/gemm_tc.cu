@@ -1,0 +1,395 @@
+// K2 / K5: fp32 GEMM on the 5th-generation tensor cores with the 3xTF32 scheme (fp32-level accuracy),
+// replacing the cuBLAS SGEMM calls behind nn.Linear in FCNN / MotionNet (nemo/neural_motion_model.py:58-71,
+// 130-148), VPoser (human_body_prior/models/vposer_model.py:63-88), the pose-blend matmul (lbs.py:229-233)
+// and their autograd backward (dgrad / wgrad).
+//
+// Persistent, warp-specialised kernel, one CTA per SM, 128 x 128 x 32 tiles:
+//   warp 0      TMA producer     cp.async.bulk.tensor of the raw fp32 A / B boxes into a 4-deep ring
+//   warps 2-3   converters       split every fp32 of the stage into tf32 hi (in place) + lo (2-deep side ring)
+//   warp 1      MMA issuer       per 8-wide k step: lo.hi + hi.lo + hi.hi via tcgen05.mma.kind::tf32 into a TMEM
+//                                partial accumulator (2 x 128 columns, double buffered)
+//   warps 4-7   accumulate +     tcgen05.ld the partial every `flush` k-blocks and add it into fp32 registers
+//               epilogue         (round-to-nearest): the tensor core accumulates with truncation, so long chains
+//                                in TMEM would cost ~K/8 * 3 * 2^-24 relative; short chains keep fp32 accuracy
+//                                for K = 20736.  Then transpose through shared memory -> bias / activation /
+//                                gate / accumulate -> coalesced 128-byte row stores (atomics under split-K).
+// Both operands may be K-major (K contiguous; 128-byte swizzle) or MN-major (M/N contiguous; 128-byte swizzle
+// with 32-byte atoms, the only MN-major layout tf32 operands support), so NN / NT / TN / TT all run without
+// a transpose pass.  M, N, K tails are handled by TMA zero fill and predicated stores.
+#include <cuda.h>  // CUtensorMap types; the driver entry point is fetched at run time (no libcuda link)
+#include <map>
+#include <mutex>
+#include <array>
+#include "common.cuh"
+#include "sm100.cuh"
+
+using namespace nb;
+using namespace nb::sm100;
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32, UMMA_K = 8;
+constexpr int NUM_THREADS = 256;   // 8 warps -> up to 255 registers per thread for the accumulate warps
+constexpr int CONV_THREADS = 64;
+constexpr int A_BYTES = BM * BK * 4;  // 16 KB
+constexpr int B_BYTES = BN * BK * 4;  // 16 KB
+constexpr int RAW_STAGES = 4, LO_STAGES = 2;
+constexpr int RAW_BYTES = A_BYTES + B_BYTES;       // [A raw -> hi][B raw -> hi]
+constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;     // one padded 32x32 transpose tile per epilogue warp
+constexpr int OFF_LO = RAW_STAGES * RAW_BYTES;
+constexpr int OFF_STAGING = OFF_LO + LO_STAGES * RAW_BYTES;
+constexpr int OFF_BARS = OFF_STAGING + STAGING_BYTES;
+constexpr int TMEM_COLS = 2 * BN;
+constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+struct GemmParams {
+  int M, N, K, ldc, act, ldg, accumulate, splits, mtiles, ntiles, kblocks, flush;
+  float gslope;
+  const float* bias;
+  const float* gate;
+  float* C;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  float* staging = reinterpret_cast<float*>(smem + OFF_STAGING);
+  const uint32_t bars = sbase + OFF_BARS;
+  auto full = [&](int s) { return bars + 8u * s; };                          // TMA landed        (tx)
+  auto conv = [&](int s) { return bars + 8u * (RAW_STAGES + s); };           // hi/lo written     (64)
+  auto empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };      // MMAs read raw/hi  (commit)
+  auto loempty = [&](int l) { return bars + 8u * (3 * RAW_STAGES + l); };    // MMAs read lo      (commit)
+  auto pfull = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 2 + b); };  // partial complete  (commit)
+  auto pempty = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 4 + b); }; // partial drained   (128)
+  const uint32_t tmem_slot = bars + 8u * (3 * RAW_STAGES + 6);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BARS + 8 * (3 * RAW_STAGES + 6));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < RAW_STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(conv(s), CONV_THREADS);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(loempty(b), 1);
+      mbar_init(pfull(b), 1);
+      mbar_init(pempty(b), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int units = p.mtiles * p.ntiles * p.splits;
+  constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  auto krange = [&](int split, int& kb0, int& kb1) {
+    kb0 = (int)((long long)split * p.kblocks / p.splits);
+    kb1 = (int)((long long)(split + 1) * p.kblocks / p.splits);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = u % p.splits, tile = u / p.splits;
+        const int mb = tile % p.mtiles, nb = tile / p.mtiles;
+        int kb0, kb1;
+        krange(split, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % RAW_STAGES;
+          const uint32_t ph = (it / RAW_STAGES) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          mbar_arrive_expect_tx(full(s), RAW_BYTES);
+          const uint32_t sa = sbase + s * RAW_BYTES, sb = sa + A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, full(s), kb * BK, mb * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * (BK * 128), &tmA, full(s), mb * BM + 32 * i, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, full(s), kb * BK, nb * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * (BK * 128), &tmB, full(s), nb * BN + 32 * i, kb * BK);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, pc = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int kb0, kb1;
+        krange(u % p.splits, kb0, kb1);
+        for (int kc = kb0; kc < kb1; kc += p.flush, ++pc) {
+          const uint32_t pb = pc & 1, pph = (pc >> 1) & 1;
+          mbar_wait(pempty(pb), pph ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + pb * BN;
+          const int kce = min(kc + p.flush, kb1);
+          for (int kb = kc; kb < kce; ++kb, ++it) {
+            const int s = it % RAW_STAGES, l = it % LO_STAGES;
+            mbar_wait(conv(s), (it / RAW_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = sbase + s * RAW_BYTES, b_hi = a_hi + A_BYTES;
+            const uint32_t a_lo = sbase + OFF_LO + l * RAW_BYTES, b_lo = a_lo + A_BYTES;
+#pragma unroll
+            for (int j = 0; j < BK / UMMA_K; ++j) {
+              const uint32_t aoff = A_MN ? j * (UMMA_K * 128) : j * (UMMA_K * 4);
+              const uint32_t boff = B_MN ? j * (UMMA_K * 128) : j * (UMMA_K * 4);
+              const uint64_t ah = A_MN ? umma_smem_desc(a_hi + aoff, BK * 128, 512, LAYOUT_SW128_BASE32B)
+                                       : umma_smem_desc(a_hi + aoff, 16, 1024, LAYOUT_SW128);
+              const uint64_t al = A_MN ? umma_smem_desc(a_lo + aoff, BK * 128, 512, LAYOUT_SW128_BASE32B)
+                                       : umma_smem_desc(a_lo + aoff, 16, 1024, LAYOUT_SW128);
+              const uint64_t bh = B_MN ? umma_smem_desc(b_hi + boff, BK * 128, 512, LAYOUT_SW128_BASE32B)
+                                       : umma_smem_desc(b_hi + boff, 16, 1024, LAYOUT_SW128);
+              const uint64_t bl = B_MN ? umma_smem_desc(b_lo + boff, BK * 128, 512, LAYOUT_SW128_BASE32B)
+                                       : umma_smem_desc(b_lo + boff, 16, 1024, LAYOUT_SW128);
+              umma_tf32(d, al, bh, idesc, (kb > kc || j > 0) ? 1u : 0u);
+              umma_tf32(d, ah, bl, idesc, 1u);
+              umma_tf32(d, ah, bh, idesc, 1u);
+            }
+            umma_commit(empty(s));    // raw/hi stage reusable once these MMAs have read it
+            umma_commit(loempty(l));  // and so is the lo slot
+          }
+          umma_commit(pfull(pb));  // partial accumulator complete
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ converters (64 threads)
+    const int ct = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int kb0, kb1;
+      krange(u % p.splits, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % RAW_STAGES, l = it % LO_STAGES;
+        float4* hi = reinterpret_cast<float4*>(smem + s * RAW_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + OFF_LO + l * RAW_BYTES);
+        mbar_wait(loempty(l), ((it / LO_STAGES) & 1) ^ 1);
+        mbar_wait(full(s), (it / RAW_STAGES) & 1);
+        // batches of 8 independent 16-byte loads, then the splits and stores (hi and lo alias as far as the
+        // compiler knows, so a load-split-store loop would serialise on shared-memory latency)
+#pragma unroll 1
+        for (int i0 = 0; i0 < RAW_BYTES / 16 / CONV_THREADS; i0 += 8) {
+          float4 x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = hi[ct + CONV_THREADS * (i0 + j)];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 h, w;
+            tf32_split4(x[j], h, w);
+            hi[ct + CONV_THREADS * (i0 + j)] = h;
+            lo[ct + CONV_THREADS * (i0 + j)] = w;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(conv(s));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ accumulate + epilogue (128 threads)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    float* st = staging + q * (32 * 33);
+    uint32_t pc = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int split = u % p.splits, tile = u / p.splits;
+      const int mb = tile % p.mtiles, nb = tile / p.mtiles;
+      int kb0, kb1;
+      krange(split, kb0, kb1);
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int kc = kb0; kc < kb1; kc += p.flush, ++pc) {
+        const uint32_t pb = pc & 1, pph = (pc >> 1) & 1;
+        mbar_wait(pfull(pb), pph);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + pb * BN;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld16(ta + c * 32, v);
+          tmem_ld16(ta + c * 32 + 16, v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(pempty(pb));  // partial drained: the MMA warp may overwrite it
+      }
+      const int m_base = mb * BM + q * 32;
+      if (m_base >= p.M) continue;  // warp-uniform
+      const int rows = min(32, p.M - m_base);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = nb * BN + c * 32;
+        if (n0 < p.N) {  // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[lane * 33 + j] = acc[c * 32 + j];
+          __syncwarp();
+          const int n = n0 + lane;
+          if (n < p.N) {
+            const float bv = (p.bias && split == 0) ? __ldg(p.bias + n) : 0.f;
+            for (int i = 0; i < rows; ++i) {
+              const size_t m = (size_t)(m_base + i);
+              float x = st[i * 33 + lane] + bv;
+              if (p.act == 1) x = fmaxf(x, 0.f);
+              else if (p.act == 2) x = x > 0.f ? x : 0.01f * x;
+              if (p.gate) x *= (__ldg(p.gate + m * p.ldg + n) > 0.f ? 1.f : p.gslope);
+              float* cp = p.C + m * p.ldc + n;
+              if (p.splits > 1) atomicAdd(cp, x);
+              else if (p.accumulate) *cp += x;
+              else *cp = x;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// row-major fp32 matrix [outer][inner] with row stride ld; box = 32 x box_outer
+int make_map(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
+             bool mn_major) {
+  static std::mutex mu;
+  static std::map<std::array<uint64_t, 6>, CUtensorMap> cache;
+  const std::array<uint64_t, 6> key = {(uint64_t)(uintptr_t)ptr, inner, outer, ld, box_outer, (uint64_t)mn_major};
+  std::lock_guard<std::mutex> lk(mu);
+  auto f = cache.find(key);
+  if (f != cache.end()) {
+    *out = f->second;
+    return 0;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled entry point unavailable");
+    return NEMO_B200_ECUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for %llu x %llu ld %llu", (int)r,
+              (unsigned long long)outer, (unsigned long long)inner, (unsigned long long)ld);
+    return NEMO_B200_ECUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    NB_CUDA(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  k_gemm_tc<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+  NB_LAUNCH_CHECK("gemm_tc");
+}
+
+}  // namespace
+
+namespace nb {
+
+// TMA needs 16-byte aligned bases and row strides; tiny problems stay on the CUDA-core kernel.
+bool gemm_tc_applicable(const float* A, const float* B, int M, int N, int K, int lda, int ldb) {
+  if (((uintptr_t)A | (uintptr_t)B) & 15) return false;
+  if ((lda | ldb) & 3) return false;
+  if (K < 8 || M < 16 || N < 8) return false;
+  return (double)M * N * K >= 2.0e6;
+}
+
+int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
+            int ldc, int transA, int transB, int act, const float* gate, int ldg, float gslope, int accumulate,
+            int force_splits, cudaStream_t s) {
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.act = act; p.ldg = ldg; p.accumulate = accumulate;
+  p.gslope = gslope; p.bias = bias; p.gate = gate; p.C = C;
+  p.mtiles = cdiv(M, BM);
+  p.ntiles = cdiv(N, BN);
+  p.kblocks = cdiv(K, BK);
+  const int tiles = p.mtiles * p.ntiles, sms = num_sms();
+  int splits = 1;
+  if (act == 0 && tiles < sms) splits = max(1, min(sms / tiles, p.kblocks / 4));
+  if (force_splits > 0) splits = (act == 0) ? min(force_splits, p.kblocks) : 1;
+  p.splits = splits;
+  // k-blocks accumulated in TMEM before the partial is folded into the fp32 registers: short reductions go in
+  // one piece (the epilogue then overlaps the next tile), deep ones in chains of 2 x 12 MMAs
+  p.flush = (cdiv(p.kblocks, splits) <= 8) ? 8 : 2;
+  if (splits > 1 && !accumulate)
+    NB_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
+  CUtensorMap ta, tb;
+  // A: transA=0 -> stored (M,K), K contiguous (K-major); transA=1 -> stored (K,M), M contiguous (MN-major)
+  int rc = transA ? make_map(&ta, A, M, K, lda, BK, true) : make_map(&ta, A, K, M, lda, BM, false);
+  if (rc) return rc;
+  // B: transB=1 -> stored (N,K), K-major; transB=0 -> stored (K,N), N contiguous (MN-major)
+  rc = transB ? make_map(&tb, B, K, N, ldb, BN, false) : make_map(&tb, B, N, K, ldb, BK, true);
+  if (rc) return rc;
+  const int grid = min(tiles * splits, sms);
+  if (transA) {
+    if (transB) return launch<true, false>(ta, tb, p, grid, s);
+    return launch<true, true>(ta, tb, p, grid, s);
+  }
+  if (transB) return launch<false, false>(ta, tb, p, grid, s);
+  return launch<false, true>(ta, tb, p, grid, s);
+}
+
+}  // namespace nb

@@ -22,6 +22,8 @@ from . import assets
 from ._lib import lib, require_cuda
 from .functional import KP_LOSSES, NV, RBF_BASES, VP, SMPLConstants, gemm
 
+LDY = 148      # row stride of the (N+1, 147) MLP output / its gradient: 16-byte rows for the TMA-fed GEMM
+LDF = 208      # row stride of the (N, 207) pose feature, same reason
 H_VP = 512     # VPoser hidden width
 L_VP = 32      # VPoser latent size
 
@@ -199,8 +201,8 @@ class FitEngine:
         nxr = self.ro['np'] + self.ro['nx']
         w = dict(
             raw=z(N), X=z(Np, self.in_dim), warped=z(N), yn=z(self.V, 3),
-            H1=z(Np, h), H2=z(Np, h), H3=z(Np, h), Y=z(Np, 147),
-            R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, 207),
+            H1=z(Np, h), H2=z(Np, h), H3=z(Np, h), Y=z(Np, LDY),
+            R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, LDF),
             PO_m=z(N, 3 * VP), PO_o=z(N, 3 * VP), PO_r=z(N, 3 * VP), dPO=z(N, 3 * VP),
             A_m=z(N, 288), A_o=z(N, 288), A_r=z(N, 288), JP=z(N, 72), JPs=z(N, 72),
             R_o=z(N, 24, 9), R_r=z(N, 24, 9),
@@ -209,7 +211,7 @@ class FitEngine:
             Rdec=z(N * 21, 9), recon=z(N, 69), signs=torch.zeros(N, 3, 2, VP // 32, dtype=torch.int32, device=d),
             ll=z(N), acc=z(8), terms=z(8), wts=z(8), total=z(1),
             d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
-            dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, 147), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.in_dim),
+            dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, LDY), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.in_dim),
             dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dbase=z(3 * VP),
             base=z(3, VP), J=z(72), vi=torch.zeros(N, dtype=torch.long, device=d),
             fi=torch.zeros(N, dtype=torch.long, device=d), noise=z(N, max(self.Cc, 1)),
@@ -241,16 +243,16 @@ class FitEngine:
         gemm(w['H1'], W(2), w['H2'], Np, h, h, h, h, h, transB=True, bias=b(2), act=1)
         # FCNN's last Linear followed by MotionNet.relu (:132)
         gemm(w['H2'], W(4), w['H3'], Np, h, h, h, h, h, transB=True, bias=b(4), act=1)
-        gemm(w['H3'], self.Whead, w['Y'], Np, 147, h, h, h, 147, transB=True, bias=self.bhead)
-        lib.rot6d_fwd(w['Y'], 147, w['R'], 216, 24, N * 24)
+        gemm(w['H3'], self.Whead, w['Y'], Np, 147, h, h, h, LDY, transB=True, bias=self.bhead)
+        lib.rot6d_fwd(w['Y'], LDY, w['R'], 216, 24, N * 24)
         lib.rotmat2aa_fwd(w['R'], 9, w['aa'], 3, 1, N * 24, 1)
         # trans - trans_0 (:3755-3766): row N of Y is the phase-0 / zero-code sample
         torch.sub(w['Y'][:N, 144:147], w['Y'][N:Np, 144:147], out=w['trans'])
 
     def _lbs_forward(self, w, N, R, PO, A, JP):
         C = self.C_
-        lib.pose_feature(R, w['F'], 207, N)
-        gemm(w['F'], C.PD, PO, N, 3 * VP, 207, 207, 3 * VP, 3 * VP)
+        lib.pose_feature(R, w['F'], LDF, N)
+        gemm(w['F'], C.PD, PO, N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
         lib.chain_fwd(R, w['J'], 0, C.parents, A, JP, N)
 
     # ------------------------------------------------------------------ the step
@@ -377,7 +379,7 @@ class FitEngine:
             # axis-angle outputs of the pose head -> rotation matrices -> 6D -> MLP output
             lib.rotmat2aa_bwd(w['R'], 9, w['d_aa'], 3, dR, 9, 1, 1, N * 24, 1)
             w['dY'].zero_()
-            lib.rot6d_bwd(w['Y'], 147, dR, 216, w['dY'], 147, 24, 0, N * 24)
+            lib.rot6d_bwd(w['Y'], LDY, dR, 216, w['dY'], LDY, 24, 0, N * 24)
             if need_2d:
                 w['dY'][:N, 144:147].copy_(w['dtr'])
                 w['dY'][N, 144:147].copy_(w['dtr'].sum(0).neg_())
@@ -414,13 +416,13 @@ class FitEngine:
         gW = lambda i: gv['learned_motion.net.net.%d.weight' % i]
         gb = lambda i: gv['learned_motion.net.net.%d.bias' % i]
         dY = w['dY']
-        gemm(dY, w['H3'], self.gWhead, 147, h, Np, 147, h, h, transA=True)
-        lib.colsum(dY, self.gbhead, Np, 147, 147, 0)
+        gemm(dY, w['H3'], self.gWhead, 147, h, Np, LDY, h, h, transA=True)
+        lib.colsum(dY, self.gbhead, Np, 147, LDY, 0)
         # d/d linear_out.bias of (trans - trans_0) cancels exactly (row N of dY is minus the column sum of the
         # rows above it); keep it an exact 0 like the reference instead of summation-order noise that Adam
         # would amplify into lr-sized steps
         self.gbhead[144:147].zero_()
-        gemm(dY, self.Whead, w['dHa'], Np, h, 147, 147, h, h, gate=w['H3'], ldg=h)
+        gemm(dY, self.Whead, w['dHa'], Np, h, 147, LDY, h, h, gate=w['H3'], ldg=h)
         gemm(w['dHa'], w['H2'], gW(4), h, h, Np, h, h, h, transA=True)
         lib.colsum(w['dHa'], gb(4), Np, h, h, 0)
         gemm(w['dHa'], W(4), w['dHb'], Np, h, h, h, h, h, gate=w['H2'], ldg=h)

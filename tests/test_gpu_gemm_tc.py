@@ -1,0 +1,103 @@
+"""tcgen05 3xTF32 GEMM (csrc/gemm_tc.cu) against float64 numpy and the CUDA-core kernel: every operand layout
+(K-major / MN-major A and B), ragged M/N/K, all fused epilogues, split-K, strided C."""
+import numpy as np
+import pytest
+import torch
+
+from .util import npy
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def G(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float32, device=DEV)
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from nemo_cvpr2023_b200._lib import lib as L
+    return L
+
+
+def pad_ld(x, mult=4):
+    """(rows, cols) -> storage with a row stride that is a multiple of `mult` floats; returns (tensor, ld)."""
+    r, c = x.shape
+    ld = (c + mult - 1) // mult * mult
+    buf = np.zeros((r, ld), np.float32)
+    buf[:, :c] = x
+    return G(buf), ld
+
+
+SHAPES = [(128, 128, 32), (4097, 1000, 1000), (300, 207, 6912), (513, 1000, 104), (147, 1000, 4097), (77, 147, 1000),
+          (4096, 2 * 3456, 207), (33, 9, 40)]
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_gemm_tc_layouts(lib, ta, tb):
+    r = np.random.RandomState(11 + 2 * ta + tb)
+    for (M, N, K) in SHAPES:
+        A = r.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+        B = r.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+        ref = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+        Ad, lda = pad_ld(A)
+        Bd, ldb = pad_ld(B)
+        C = torch.full((M, N), 7.0, device=DEV)
+        lib.gemm_tc(Ad, Bd, None, C, M, N, K, lda, ldb, N, ta, tb, 0, None, 0, 0.0, 0, 1)
+        torch.cuda.synchronize()
+        err = np.abs(npy(C) - ref).max() / np.abs(ref).max()
+        # 3xTF32: ~2^-21 relative per product, fp32 accumulation
+        assert err < 4e-6, 'gemm_tc ta=%d tb=%d %s: rel-max err %.3e' % (ta, tb, (M, N, K), err)
+
+
+def test_gemm_tc_epilogues_and_splitk(lib):
+    r = np.random.RandomState(3)
+    M, N, K = 1000, 207, 2080
+    A = r.standard_normal((M, K)).astype(np.float32)
+    B = r.standard_normal((N, K)).astype(np.float32)
+    bias = r.standard_normal(N).astype(np.float32)
+    gate = r.standard_normal((M, N)).astype(np.float32)
+    C0 = r.standard_normal((M, 216)).astype(np.float32)
+    acc = A.astype(np.float64) @ B.T.astype(np.float64)
+    Ad, Bd = G(A), G(B)
+    # bias + leaky relu
+    C = torch.empty(M, N, device=DEV)
+    lib.gemm_tc(Ad, Bd, G(bias), C, M, N, K, K, K, N, 0, 1, 2, None, 0, 0.0, 0, 0)
+    ref = acc + bias
+    ref = np.where(ref > 0, ref, 0.01 * ref)
+    assert np.abs(npy(C) - ref).max() / np.abs(ref).max() < 4e-6
+    # bias + relu
+    lib.gemm_tc(Ad, Bd, G(bias), C, M, N, K, K, K, N, 0, 1, 1, None, 0, 0.0, 0, 0)
+    assert np.abs(npy(C) - np.maximum(acc + bias, 0)).max() / np.abs(ref).max() < 4e-6
+    # gate (activation backward) + accumulate into a strided C, with and without split-K
+    for splits in (1, 5):
+        Cs = G(C0)
+        lib.gemm_tc(Ad, Bd, None, Cs, M, N, K, K, K, 216, 0, 1, 0, G(gate), N, 0.01, 1, splits)
+        ref = C0.astype(np.float64).copy()
+        ref[:, :N] += acc * np.where(gate > 0, 1.0, 0.01)
+        assert np.abs(npy(Cs) - ref).max() / np.abs(ref).max() < 4e-6, 'splits=%d' % splits
+    # split-K overwrite (the kernel zeroes the N used columns only) + bias
+    Cs = G(C0)
+    lib.gemm_tc(Ad, Bd, G(bias), Cs, M, N, K, K, K, 216, 0, 1, 0, None, 0, 0.0, 0, 4)
+    ref = C0.astype(np.float64).copy()
+    ref[:, :N] = acc + bias
+    assert np.abs(npy(Cs) - ref).max() / np.abs(ref).max() < 4e-6
+    # heuristic split (wgrad-like: small M x N, deep K)
+    M2, N2, K2 = 147, 1000, 4097
+    A2 = r.standard_normal((K2, 148)).astype(np.float32)
+    B2 = r.standard_normal((K2, N2)).astype(np.float32)
+    C = torch.empty(M2, N2, device=DEV)
+    lib.gemm_tc(G(A2), G(B2), None, C, M2, N2, K2, 148, N2, N2, 1, 0, 0, None, 0, 0.0, 0, 0)
+    ref = A2[:, :M2].T.astype(np.float64) @ B2.astype(np.float64)
+    assert np.abs(npy(C) - ref).max() / np.abs(ref).max() < 4e-6
+
+
+def test_gemm_dispatch_agrees_with_cuda_core_kernel(lib):
+    """nemo_b200_gemm (tensor-core path for these shapes) vs nemo_b200_gemm_simt on the same inputs."""
+    r = np.random.RandomState(9)
+    M, N, K = 512, 20736, 208
+    A, B = G(r.standard_normal((M, K))), G(0.001 * r.standard_normal((K, N)))
+    C1, C2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    lib.gemm(A, B, None, C1, M, N, K, K, N, N, 0, 0, 0, None, 0, 0.0, 0)
+    lib.gemm_simt(A, B, None, C2, M, N, K, K, N, N, 0, 0, 0, None, 0, 0.0, 0)
+    assert (C1 - C2).abs().max().item() < 4e-6 * C2.abs().max().item()
