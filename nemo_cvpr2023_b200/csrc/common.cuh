@@ -64,6 +64,32 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Reduce K (power of two <= 32) per-lane values across the warp; on return v[0] of lane l holds the
+// total of value index (l & (K-1)) ... for K == 32 that is value l.  31 shuffles for K = 32.
+template <int K>
+__device__ __forceinline__ void warp_reduce_scatter(float* v, int lane) {
+  int off = 16;
+#pragma unroll
+  for (int half = K / 2; half >= 1; half >>= 1, off >>= 1) {
+    bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float send = upper ? v[i] : v[i + half];
+      float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+// index of the value that lane ends up holding after warp_reduce_scatter<K>
+template <int K>
+__device__ __forceinline__ int scatter_index(int lane) {
+  if (K == 32) return lane;
+  if (K == 4) return ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+  return 0;
+}
+
 #endif
 
 }  // namespace nb
