@@ -16,6 +16,7 @@
 // Both operands may be K-major (K contiguous; 128-byte swizzle) or MN-major (M/N contiguous; 128-byte swizzle
 // with 32-byte atoms, the only MN-major layout tf32 operands support), so NN / NT / TN / TT all run without
 // a transpose pass.  M, N, K tails are handled by TMA zero fill and predicated stores.
+#include <stdlib.h>
 #include <cuda.h>  // CUtensorMap types; the driver entry point is fetched at run time (no libcuda link)
 #include <map>
 #include <mutex>
@@ -44,7 +45,7 @@ constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct GemmParams {
-  int M, N, K, ldc, act, ldg, accumulate, splits, mtiles, ntiles, kblocks, flush;
+  int M, N, K, ldc, act, ldg, accumulate, splits, mtiles, ntiles, kblocks, flush, hw_trunc;
   float gslope;
   const float* bias;
   const float* gate;
@@ -58,7 +59,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
-  float* staging = reinterpret_cast<float*>(smem + OFF_STAGING);
   const uint32_t bars = sbase + OFF_BARS;
   auto full = [&](int s) { return bars + 8u * s; };                          // TMA landed        (tx)
   auto conv = [&](int s) { return bars + 8u * (RAW_STAGES + s); };           // hi/lo written     (64)
@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   auto pfull = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 2 + b); };  // partial complete  (commit)
   auto pempty = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 4 + b); }; // partial drained   (128)
   const uint32_t tmem_slot = bars + 8u * (3 * RAW_STAGES + 6);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BARS + 8 * (3 * RAW_STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = lds32u(tmem_slot);
 
   const int units = p.mtiles * p.ntiles * p.splits;
   constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
@@ -148,18 +147,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             tc_fence_after();
             const uint32_t a_hi = sbase + s * RAW_BYTES, b_hi = a_hi + A_BYTES;
             const uint32_t a_lo = sbase + OFF_LO + l * RAW_BYTES, b_lo = a_lo + A_BYTES;
+            const uint64_t ah0 = A_MN ? umma_smem_desc(a_hi, BK * 128, 512, LAYOUT_SW128_BASE32B)
+                                      : umma_smem_desc(a_hi, 16, 1024, LAYOUT_SW128);
+            const uint64_t bh0 = B_MN ? umma_smem_desc(b_hi, BK * 128, 512, LAYOUT_SW128_BASE32B)
+                                      : umma_smem_desc(b_hi, 16, 1024, LAYOUT_SW128);
+            const uint64_t al0 = umma_desc_advance(ah0, a_lo - a_hi), bl0 = umma_desc_advance(bh0, b_lo - b_hi);
 #pragma unroll
             for (int j = 0; j < BK / UMMA_K; ++j) {
-              const uint32_t aoff = A_MN ? j * (UMMA_K * 128) : j * (UMMA_K * 4);
-              const uint32_t boff = B_MN ? j * (UMMA_K * 128) : j * (UMMA_K * 4);
-              const uint64_t ah = A_MN ? umma_smem_desc(a_hi + aoff, BK * 128, 512, LAYOUT_SW128_BASE32B)
-                                       : umma_smem_desc(a_hi + aoff, 16, 1024, LAYOUT_SW128);
-              const uint64_t al = A_MN ? umma_smem_desc(a_lo + aoff, BK * 128, 512, LAYOUT_SW128_BASE32B)
-                                       : umma_smem_desc(a_lo + aoff, 16, 1024, LAYOUT_SW128);
-              const uint64_t bh = B_MN ? umma_smem_desc(b_hi + boff, BK * 128, 512, LAYOUT_SW128_BASE32B)
-                                       : umma_smem_desc(b_hi + boff, 16, 1024, LAYOUT_SW128);
-              const uint64_t bl = B_MN ? umma_smem_desc(b_lo + boff, BK * 128, 512, LAYOUT_SW128_BASE32B)
-                                       : umma_smem_desc(b_lo + boff, 16, 1024, LAYOUT_SW128);
+              constexpr uint32_t ASTEP = A_MN ? UMMA_K * 128 : UMMA_K * 4, BSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 4;
+              const uint64_t ah = umma_desc_advance(ah0, j * ASTEP), al = umma_desc_advance(al0, j * ASTEP);
+              const uint64_t bh = umma_desc_advance(bh0, j * BSTEP), bl = umma_desc_advance(bl0, j * BSTEP);
               umma_tf32(d, al, bh, idesc, (kb > kc || j > 0) ? 1u : 0u);
               umma_tf32(d, ah, bl, idesc, 1u);
               umma_tf32(d, ah, bh, idesc, 1u);
@@ -181,24 +178,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       krange(u % p.splits, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % RAW_STAGES, l = it % LO_STAGES;
-        float4* hi = reinterpret_cast<float4*>(smem + s * RAW_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem + OFF_LO + l * RAW_BYTES);
+        const uint32_t hi = sbase + s * RAW_BYTES + 16 * ct, lo = sbase + OFF_LO + l * RAW_BYTES + 16 * ct;
+        constexpr uint32_t CS = 16 * CONV_THREADS;
         mbar_wait(loempty(l), ((it / LO_STAGES) & 1) ^ 1);
         mbar_wait(full(s), (it / RAW_STAGES) & 1);
-        // batches of 8 independent 16-byte loads, then the splits and stores (hi and lo alias as far as the
-        // compiler knows, so a load-split-store loop would serialise on shared-memory latency)
-#pragma unroll 1
-        for (int i0 = 0; i0 < RAW_BYTES / 16 / CONV_THREADS; i0 += 8) {
-          float4 x[8];
+        // software pipelined over batches of 8 independent 16-byte loads: the next batch is in flight while the
+        // current one is split and stored (hi and lo alias as far as the compiler knows, so a plain
+        // load-split-store loop would serialise on shared-memory latency)
+        constexpr int NB8 = RAW_BYTES / 16 / CONV_THREADS / 8;
+        float4 x[8], y[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = hi[ct + CONV_THREADS * (i0 + j)];
+        for (int j = 0; j < 8; ++j) x[j] = lds128(hi + CS * j);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 h, w;
-            tf32_split4(x[j], h, w);
-            hi[ct + CONV_THREADS * (i0 + j)] = h;
-            lo[ct + CONV_THREADS * (i0 + j)] = w;
+        for (int bt = 0; bt < NB8; ++bt) {
+          if (bt + 1 < NB8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = lds128(hi + CS * (8 * (bt + 1) + j));
           }
+          if (p.hw_trunc) {
+            // the tensor core ignores the low 13 mantissa bits of a tf32 operand: the raw fp32 tile is the hi
+            // operand as it stands, only lo = x - trunc(x) is written
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 w;
+              w.x = x[j].x - __uint_as_float(__float_as_uint(x[j].x) & 0xffffe000u);
+              w.y = x[j].y - __uint_as_float(__float_as_uint(x[j].y) & 0xffffe000u);
+              w.z = x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xffffe000u);
+              w.w = x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xffffe000u);
+              sts128(lo + CS * (8 * bt + j), w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 h, w;
+              tf32_split4(x[j], h, w);
+              sts128(hi + CS * (8 * bt + j), h);
+              sts128(lo + CS * (8 * bt + j), w);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = y[j];
         }
         fence_proxy_async_smem();
         mbar_arrive(conv(s));
@@ -207,7 +226,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   } else {
     // ------------------------------------------------------------------ accumulate + epilogue (128 threads)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    float* st = staging + q * (32 * 33);
+    const uint32_t st = sbase + OFF_STAGING + q * (32 * 33 * 4);
     uint32_t pc = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int split = u % p.splits, tile = u / p.splits;
@@ -242,14 +261,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
         const int n0 = nb * BN + c * 32;
         if (n0 < p.N) {  // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 32; ++j) st[lane * 33 + j] = acc[c * 32 + j];
+          for (int j = 0; j < 32; ++j) sts32(st + 4 * (lane * 33 + j), acc[c * 32 + j]);
           __syncwarp();
           const int n = n0 + lane;
           if (n < p.N) {
             const float bv = (p.bias && split == 0) ? __ldg(p.bias + n) : 0.f;
             for (int i = 0; i < rows; ++i) {
               const size_t m = (size_t)(m_base + i);
-              float x = st[i * 33 + lane] + bv;
+              float x = lds32(st + 4 * (i * 33 + lane)) + bv;
               if (p.act == 1) x = fmaxf(x, 0.f);
               else if (p.act == 2) x = x > 0.f ? x : 0.01f * x;
               if (p.gate) x *= (__ldg(p.gate + m * p.ldg + n) > 0.f ? 1.f : p.gslope);
@@ -374,6 +393,10 @@ int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, 
   // k-blocks accumulated in TMEM before the partial is folded into the fp32 registers: short reductions go in
   // one piece (the epilogue then overlaps the next tile), deep ones in chains of 2 x 12 MMAs
   p.flush = (cdiv(p.kblocks, splits) <= 8) ? 8 : 2;
+  // measured on B200: tcgen05.mma.kind::tf32 ignores the low 13 mantissa bits of its operands, so the raw fp32
+  // tile serves as the hi part (NEMO_B200_GEMM_HWTRUNC=0 selects the explicit round-and-rewrite variant)
+  static const int hw_trunc = [] { const char* e = getenv("NEMO_B200_GEMM_HWTRUNC"); return e ? atoi(e) : 1; }();
+  p.hw_trunc = hw_trunc;
   if (splits > 1 && !accumulate)
     NB_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
   CUtensorMap ta, tb;

@@ -32,12 +32,12 @@ __device__ __forceinline__ uint32_t kmajor_sw128(int row, int k) {
   return (uint32_t)(row * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2));
 }
 
-// MODE 0: forward, one mesh (2 CTAs per SM: 81 KB shared memory, 256 TMEM columns each).
-// MODE 1: fused L1 of two meshes (mesh a | mesh b side by side in one accumulator; 1 CTA per SM).
-// Both work on groups of FB = 8 frames.
+// MODE 0: forward, one mesh, groups of 8 frames.
+// MODE 1: fused L1 of two meshes (mesh a | mesh b side by side in one accumulator), groups of 4 frames.
+// Either way 96 accumulator columns, 81 KB of shared memory and 256 TMEM columns: 2 CTAs per SM.
 template <int MODE>
 struct SkinCfg {
-  static constexpr int FB = 8;
+  static constexpr int FB = MODE == 0 ? 8 : 4;
   static constexpr int NMESH = MODE == 0 ? 1 : 2;
   static constexpr int NCOL = NMESH * FB * 12;     // accumulator columns = B operand rows (96 / 192)
   static constexpr int BUF_COLS = NCOL <= 128 ? 128 : 256;  // TMEM column stride between the two accumulators
@@ -48,7 +48,7 @@ struct SkinCfg {
   static constexpr int OFF_BARS = OFF_RED + 256;
   static constexpr int SMEM_BYTES = OFF_BARS + 64 + 1024;
   static constexpr int TMEM_COLS = 2 * BUF_COLS;
-  static constexpr int CTAS_PER_SM = MODE == 0 ? 2 : 1;
+  static constexpr int CTAS_PER_SM = 2;
 };
 
 struct SkinArgs {
@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(256, SkinCfg<MODE>::CTAS_PER_SM) k_skin_tc_fwd
   auto tempty = [&](int b) { return bars + 8u * (2 + b); };  // workers done reading T[b]       (128)
   auto amfree = [&](int b) { return bars + 8u * (4 + b); };  // MMAs done reading Amat[b]       (commit)
   const uint32_t tmem_slot = bars + 48;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C_::OFF_BARS + 48);
-  float* sred = reinterpret_cast<float*>(smem + C_::OFF_RED);
+  const uint32_t sred = sbase + C_::OFF_RED;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vt = blockIdx.x % NT_V, chunk = blockIdx.x / NT_V;
@@ -103,7 +102,7 @@ __global__ void __launch_bounds__(256, SkinCfg<MODE>::CTAS_PER_SM) k_skin_tc_fwd
   if (warp == 4) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   // zero both B-operand buffers once: the k = 24..31 pad columns stay zero for the whole kernel
   for (int i = tid; i < 4 * C_::AM_BYTES / 16; i += 256)
-    reinterpret_cast<float4*>(smem + C_::OFF_AM)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sts128(sbase + C_::OFF_AM + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   // W tile -> tf32 hi / lo, K-major (row = vertex, k = joint), pad columns zero
   if (tid < TILE_V) {
     const int v = v0 + tid;
@@ -111,16 +110,16 @@ __global__ void __launch_bounds__(256, SkinCfg<MODE>::CTAS_PER_SM) k_skin_tc_fwd
     for (int k = 0; k < 32; ++k) {
       float w = k < NJ ? __ldg(a.Wt + (size_t)k * VP + v) : 0.f, hi, lo;
       tf32_split(w, hi, lo);
-      const uint32_t off = kmajor_sw128(tid, k);
-      *reinterpret_cast<float*>(smem + C_::OFF_W + off) = hi;
-      *reinterpret_cast<float*>(smem + C_::OFF_W + WT_BYTES + off) = lo;
+      const uint32_t off = sbase + C_::OFF_W + kmajor_sw128(tid, k);
+      sts32(off, hi);
+      sts32(off + WT_BYTES, lo);
     }
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = lds32u(tmem_slot);
   constexpr uint32_t idesc = umma_idesc_tf32(128, NCOL, 0, 0);
 
   if (warp >= 4) {
@@ -130,7 +129,7 @@ __global__ void __launch_bounds__(256, SkinCfg<MODE>::CTAS_PER_SM) k_skin_tc_fwd
       const int b = gi & 1;
       const uint32_t use = gi >> 1;  // how many times buffer b was used before
       if (use > 0) mbar_wait(amfree(b), (use - 1) & 1);
-      uint8_t* am = smem + C_::OFF_AM + b * 2 * C_::AM_BYTES;
+      const uint32_t am = sbase + C_::OFF_AM + b * 2 * C_::AM_BYTES;
       const int n0 = group_of(gi) * FB;
       // all loads of the group first (independent, L2 latency overlapped), then split + scatter into the operand
       constexpr int ITER = NMESH * FB * 288 / 128;
@@ -149,9 +148,9 @@ __global__ void __launch_bounds__(256, SkinCfg<MODE>::CTAS_PER_SM) k_skin_tc_fwd
         const int f = r / 288, jc = r % 288, j = jc / 12, c = jc % 12;
         float hi, lo;
         tf32_split(x[i], hi, lo);
-        const uint32_t off = kmajor_sw128((mesh * FB + f) * 12 + c, j);
-        *reinterpret_cast<float*>(am + off) = hi;
-        *reinterpret_cast<float*>(am + C_::AM_BYTES + off) = lo;
+        const uint32_t off = am + kmajor_sw128((mesh * FB + f) * 12 + c, j);
+        sts32(off, hi);
+        sts32(off + C_::AM_BYTES, lo);
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -159,14 +158,12 @@ __global__ void __launch_bounds__(256, SkinCfg<MODE>::CTAS_PER_SM) k_skin_tc_fwd
         if (use > 0) mbar_wait(tempty(b), (use - 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + b * C_::BUF_COLS;
-        const uint32_t w_hi = sbase + C_::OFF_W, w_lo = w_hi + WT_BYTES;
-        const uint32_t m_hi = sbase + C_::OFF_AM + b * 2 * C_::AM_BYTES, m_lo = m_hi + C_::AM_BYTES;
+        const uint64_t wh0 = umma_smem_desc(sbase + C_::OFF_W, 16, 1024, LAYOUT_SW128);
+        const uint64_t mh0 = umma_smem_desc(sbase + C_::OFF_AM + b * 2 * C_::AM_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {  // K = 24 = 3 steps of 8
-          const uint64_t wh = umma_smem_desc(w_hi + j * 32, 16, 1024, LAYOUT_SW128);
-          const uint64_t wl = umma_smem_desc(w_lo + j * 32, 16, 1024, LAYOUT_SW128);
-          const uint64_t mh = umma_smem_desc(m_hi + j * 32, 16, 1024, LAYOUT_SW128);
-          const uint64_t ml = umma_smem_desc(m_lo + j * 32, 16, 1024, LAYOUT_SW128);
+          const uint64_t wh = umma_desc_advance(wh0, j * 32), wl = umma_desc_advance(wh0, WT_BYTES + j * 32);
+          const uint64_t mh = umma_desc_advance(mh0, j * 32), ml = umma_desc_advance(mh0, C_::AM_BYTES + j * 32);
           umma_tf32(d, wl, mh, idesc, j > 0 ? 1u : 0u);
           umma_tf32(d, wh, ml, idesc, 1u);
           umma_tf32(d, wh, mh, idesc, 1u);
@@ -280,9 +277,9 @@ __global__ void __launch_bounds__(256, SkinCfg<MODE>::CTAS_PER_SM) k_skin_tc_fwd
     }
     if (MODE == 1) {
       l1 = warp_sum(l1);
-      if (lane == 0) sred[warp] = l1;
+      if (lane == 0) sts32(sred + 4 * warp, l1);
       asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (tid == 0) atomicAdd(a.l1_sum, sred[0] + sred[1] + sred[2] + sred[3]);
+      if (tid == 0) atomicAdd(a.l1_sum, lds32(sred) + lds32(sred + 4) + lds32(sred + 8) + lds32(sred + 12));
     }
   }
   tc_fence_before();
@@ -331,7 +328,7 @@ struct SkinBwdArgs {
 };
 
 template <int NXR>
-__global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
+__global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
   using C_ = BwdCfg;
   constexpr int FB = C_::FB;
   extern __shared__ uint8_t smem_raw[];
@@ -347,8 +344,7 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
   const uint32_t gfree = bars + 88;                             // dA-GEMM done reading G^T      (commit)
   auto djfull = [&](int b) { return bars + 8u * (12 + b); };    // joint gradients staged        (96)
   const uint32_t tmem_slot = bars + 112;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C_::OFF_BARS + 112);
-  float* sdj = reinterpret_cast<float*>(smem + C_::OFF_DJ);
+  const uint32_t sdj = sbase + C_::OFF_DJ;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vt = blockIdx.x % NT_V, chunk = blockIdx.x / NT_V;
@@ -363,20 +359,20 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
-      mbar_init(tempty(b), 128);
+      mbar_init(tempty(b), 256);
       mbar_init(amfree(b), 1);
       mbar_init(d2full(b), 1);
       mbar_init(d2empty(b), 96);
       mbar_init(djfull(b), 96);
     }
-    mbar_init(gfull, 128);
+    mbar_init(gfull, 256);
     mbar_init(gfree, 1);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   // zero Amat (pad columns k = 24..31), G^T and its tail
-  for (int i = tid; i < (C_::OFF_DJ - C_::OFF_AM) / 16; i += 256)
-    reinterpret_cast<float4*>(smem + C_::OFF_AM)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < (C_::OFF_DJ - C_::OFF_AM) / 16; i += 384)
+    sts128(sbase + C_::OFF_AM + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   if (tid < TILE_V) {
     const int v = v0 + tid;
 #pragma unroll
@@ -384,20 +380,20 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
       float w = k < NJ ? __ldg(a.Wt + (size_t)k * VP + v) : 0.f, hi, lo;
       tf32_split(w, hi, lo);
       // T-GEMM A operand: row = vertex, k = joint
-      const uint32_t o1 = kmajor_sw128(tid, k);
-      *reinterpret_cast<float*>(smem + C_::OFF_WT + o1) = hi;
-      *reinterpret_cast<float*>(smem + C_::OFF_WT + WT_BYTES + o1) = lo;
+      const uint32_t o1 = sbase + C_::OFF_WT + kmajor_sw128(tid, k);
+      sts32(o1, hi);
+      sts32(o1 + WT_BYTES, lo);
       // dA-GEMM B operand: row = joint, k = vertex (k-block = warp, 32 rows x 128 bytes each)
-      const uint32_t o2 = (uint32_t)(warp * 4096) + kmajor_sw128(k, lane);
-      *reinterpret_cast<float*>(smem + C_::OFF_WD + o2) = hi;
-      *reinterpret_cast<float*>(smem + C_::OFF_WD + C_::WD_BYTES + o2) = lo;
+      const uint32_t o2 = sbase + C_::OFF_WD + (uint32_t)(warp * 4096) + kmajor_sw128(k, lane);
+      sts32(o2, hi);
+      sts32(o2 + C_::WD_BYTES, lo);
     }
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = lds32u(tmem_slot);
   constexpr uint32_t idesc_t = umma_idesc_tf32(128, C_::NROW, 0, 0);
   constexpr uint32_t idesc_d = umma_idesc_tf32(128, 32, 0, 0);
 
@@ -428,7 +424,7 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
       const int b = gi & 1;
       const uint32_t use = gi >> 1;
       if (use > 0) mbar_wait(amfree(b), (use - 1) & 1);
-      uint8_t* am = smem + C_::OFF_AM + b * 2 * C_::AM_BYTES;
+      const uint32_t am = sbase + C_::OFF_AM + b * 2 * C_::AM_BYTES;
       const int n0 = group_of(gi) * FB;
       constexpr int ITER = FB * 288 / 96;
       float x[ITER], dj[FB];
@@ -442,7 +438,7 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
       for (int f = 0; f < FB; ++f)
         dj[f] = (a.dJX && pt < nxr3 && n0 + f < a.N) ? __ldg(a.dJX + (size_t)(n0 + f) * nxr3 + pt) : 0.f;
 #pragma unroll
-      for (int f = 0; f < FB; ++f) sdj[(b * FB + f) * 96 + pt] = dj[f];
+      for (int f = 0; f < FB; ++f) sts32(sdj + 4 * ((b * FB + f) * 96 + pt), dj[f]);
       mbar_arrive(djfull(b));
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
@@ -450,9 +446,9 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
         const int f = e / 288, jc = e % 288, j = jc / 12, c = jc % 12;
         float hi, lo;
         tf32_split(x[i], hi, lo);
-        const uint32_t off = kmajor_sw128(f * 12 + c, j);
-        *reinterpret_cast<float*>(am + off) = hi;
-        *reinterpret_cast<float*>(am + C_::AM_BYTES + off) = lo;
+        const uint32_t off = am + kmajor_sw128(f * 12 + c, j);
+        sts32(off, hi);
+        sts32(off + C_::AM_BYTES, lo);
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 96;" ::: "memory");
@@ -460,14 +456,12 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
         if (use > 0) mbar_wait(tempty(b), (use - 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + b * 128;
-        const uint32_t w_hi = sbase + C_::OFF_WT, w_lo = w_hi + WT_BYTES;
-        const uint32_t m_hi = sbase + C_::OFF_AM + b * 2 * C_::AM_BYTES, m_lo = m_hi + C_::AM_BYTES;
+        const uint64_t wh0 = umma_smem_desc(sbase + C_::OFF_WT, 16, 1024, LAYOUT_SW128);
+        const uint64_t mh0 = umma_smem_desc(sbase + C_::OFF_AM + b * 2 * C_::AM_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const uint64_t wh = umma_smem_desc(w_hi + j * 32, 16, 1024, LAYOUT_SW128);
-          const uint64_t wl = umma_smem_desc(w_lo + j * 32, 16, 1024, LAYOUT_SW128);
-          const uint64_t mh = umma_smem_desc(m_hi + j * 32, 16, 1024, LAYOUT_SW128);
-          const uint64_t ml = umma_smem_desc(m_lo + j * 32, 16, 1024, LAYOUT_SW128);
+          const uint64_t wh = umma_desc_advance(wh0, j * 32), wl = umma_desc_advance(wh0, WT_BYTES + j * 32);
+          const uint64_t mh = umma_desc_advance(mh0, j * 32), ml = umma_desc_advance(mh0, C_::AM_BYTES + j * 32);
           umma_tf32(d, wl, mh, idesc_t, j > 0 ? 1u : 0u);
           umma_tf32(d, wh, ml, idesc_t, 1u);
           umma_tf32(d, wh, mh, idesc_t, 1u);
@@ -481,6 +475,8 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
   } else if (warp == 7) {
     // ------------------------------------------------------------------ dA-GEMM issuer
     if (lane == 0) {
+      const uint64_t gh0 = umma_smem_desc(sbase + C_::OFF_GT, 16, 1024, LAYOUT_SW128);
+      const uint64_t wd0 = umma_smem_desc(sbase + C_::OFF_WD, 16, 1024, LAYOUT_SW128);
       for (int gi = 0; gi < ng; ++gi) {
         const int b = gi & 1;
         const uint32_t use = gi >> 1;
@@ -488,17 +484,13 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
         if (use > 0) mbar_wait(d2empty(b), (use - 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + 256 + b * 32;
-        const uint32_t g_hi = sbase + C_::OFF_GT, g_lo = g_hi + C_::GT_BYTES;
-        const uint32_t w_hi = sbase + C_::OFF_WD, w_lo = w_hi + C_::WD_BYTES;
-#pragma unroll 1
+#pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t go = kb * C_::GT_KB_BYTES + ks * 32, wo = kb * 4096 + ks * 32;
-            const uint64_t gh = umma_smem_desc(g_hi + go, 16, 1024, LAYOUT_SW128);
-            const uint64_t gl = umma_smem_desc(g_lo + go, 16, 1024, LAYOUT_SW128);
-            const uint64_t wh = umma_smem_desc(w_hi + wo, 16, 1024, LAYOUT_SW128);
-            const uint64_t wl = umma_smem_desc(w_lo + wo, 16, 1024, LAYOUT_SW128);
+            const uint64_t gh = umma_desc_advance(gh0, go), gl = umma_desc_advance(gh0, C_::GT_BYTES + go);
+            const uint64_t wh = umma_desc_advance(wd0, wo), wl = umma_desc_advance(wd0, C_::WD_BYTES + wo);
             umma_tf32(d, gl, wh, idesc_d, (kb | ks) ? 1u : 0u);
             umma_tf32(d, gh, wl, idesc_d, 1u);
             umma_tf32(d, gh, wh, idesc_d, 1u);
@@ -510,8 +502,13 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ workers: one thread per vertex
-    const int v = v0 + tid;
+    // ------------------------------------------------------------------ workers: two threads per vertex
+    // warps 0-3 take frames 0-3 of every group, warps 8-11 frames 4-7 (same TMEM lane quarter = warp & 3):
+    // two worker warps per scheduler, so one hides the other's TMEM / shared-memory latencies
+    constexpr int FH = FB / 2;
+    const int wq = warp & 3, half = warp >> 3;
+    const int vl = wq * 32 + lane;  // vertex within the tile
+    const int v = v0 + vl;
     const bool real = v < NV;
     float bs[3];
 #pragma unroll
@@ -520,23 +517,20 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
 #pragma unroll
     for (int r = 0; r < NXR; ++r) jx[r] = r < a.nx ? __ldg(a.Jx + (size_t)r * VP + v) : 0.f;
     const int sl = a.slot ? a.slot[v] : -1;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    uint8_t* gt = smem + C_::OFF_GT + warp * C_::GT_KB_BYTES;  // this warp's k-block of G^T (hi part)
-    float po[FB][3], pn[FB][3], dv[FB][3], dn[FB][3];
-    uint32_t sw[2] = {0u, 0u}, swn[2] = {0u, 0u};  // the group's 48 sign words, one or two per lane
-    auto load_in = [&](int gi, float (&p)[FB][3], float (&d)[FB][3], uint32_t (&w)[2]) {
-      const int n0 = gi < ng ? group_of(gi) * FB : a.N;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const uint32_t gt = sbase + C_::OFF_GT + wq * C_::GT_KB_BYTES;  // this quarter's k-block of G^T (hi part)
+    float po[FH][3], pn[FH][3], dv[FH][3], dn[FH][3];
+    uint32_t sw = 0u, swn = 0u;  // this half's 24 sign words, one per lane
+    auto load_in = [&](int gi, float (&p)[FH][3], float (&d)[FH][3], uint32_t& w) {
+      const int n0 = gi < ng ? group_of(gi) * FB + half * FH : a.N;
       if (a.signs) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int wi = lane + 32 * h, fc = wi >> 1;  // word (f*3 + c)*2 + {pos, neg}
-          const int n = n0 + fc / 3;
-          w[h] = (wi < FB * 6 && n < a.N)
-                     ? __ldg(a.signs + (((size_t)n * 3 + fc % 3) * 2 + (wi & 1)) * (VP / 32) + (v >> 5)) : 0u;
-        }
+        const int fc = lane >> 1;  // word (f*3 + c)*2 + {pos, neg}
+        const int n = n0 + fc / 3;
+        w = (lane < FH * 6 && n < a.N)
+                ? __ldg(a.signs + (((size_t)n * 3 + fc % 3) * 2 + (lane & 1)) * (VP / 32) + (v >> 5)) : 0u;
       }
 #pragma unroll
-      for (int f = 0; f < FB; ++f) {
+      for (int f = 0; f < FH; ++f) {
         const int n = n0 + f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -548,62 +542,61 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
     load_in(0, po, dv, sw);
     for (int gi = 0; gi < ng; ++gi) {
       const int b = gi & 1;
-      const int n0 = group_of(gi) * FB;
+      const int n0 = group_of(gi) * FB + half * FH;
       load_in(gi + 1, pn, dn, swn);
       if (a.dJX) mbar_wait(djfull(b), (gi >> 1) & 1);
       // ---- upstream gradient of every vertex of the group: dV + sign bits + joint read-outs
 #pragma unroll
-      for (int f = 0; f < FB; ++f) {
+      for (int f = 0; f < FH; ++f) {
         const int n = n0 + f;
         if (n < a.N) {  // warp-uniform
           if (a.signs) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              constexpr int dummy = 0; (void)dummy;
-              const int wi = (f * 3 + c) * 2;
-              const uint32_t pm = __shfl_sync(0xffffffffu, sw[wi >> 5], wi & 31);
-              const uint32_t nm = __shfl_sync(0xffffffffu, sw[(wi + 1) >> 5], (wi + 1) & 31);
+              const uint32_t pm = __shfl_sync(0xffffffffu, sw, (f * 3 + c) * 2);
+              const uint32_t nm = __shfl_sync(0xffffffffu, sw, (f * 3 + c) * 2 + 1);
               dv[f][c] += a.sign_scale * ((float)((pm >> lane) & 1u) - (float)((nm >> lane) & 1u));
             }
           }
           if (a.dJX) {
-            const float* dj = sdj + (b * FB + f) * 96;
-            if (sl >= 0) { dv[f][0] += dj[sl * 3]; dv[f][1] += dj[sl * 3 + 1]; dv[f][2] += dj[sl * 3 + 2]; }
+            const uint32_t dj = sdj + 4 * ((b * FB + half * FH + f) * 96);
+            if (sl >= 0) { dv[f][0] += lds32(dj + 12 * sl); dv[f][1] += lds32(dj + 12 * sl + 4); dv[f][2] += lds32(dj + 12 * sl + 8); }
 #pragma unroll
             for (int r = 0; r < NXR; ++r) {
               if (r < a.nx) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) dv[f][c] += jx[r] * dj[(a.np + r) * 3 + c];
+                for (int c = 0; c < 3; ++c) dv[f][c] += jx[r] * lds32(dj + 4 * ((a.np + r) * 3 + c));
               }
             }
           }
         }
       }
-      // ---- dPO = R^T dv from the T rows in TMEM
+      // ---- dPO = R^T dv from the T rows in TMEM (all of this half's rows in one batch of loads)
       mbar_wait(tfull(b), (gi >> 1) & 1);
       tc_fence_after();
-      const uint32_t ta = tmem_base + lane_addr + b * 128;
+      const uint32_t ta = tmem_base + lane_addr + b * 128 + half * (FH * 12);
+      uint32_t t[FH * 12];
+      tmem_ld16(ta, t);
+      tmem_ld16(ta + 16, t + 16);
+      tmem_ld16(ta + 32, t + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty(b));
 #pragma unroll
-      for (int f = 0; f < FB; ++f) {
+      for (int f = 0; f < FH; ++f) {
         const int n = n0 + f;
-        uint32_t t[12];
-        tmem_ld4(ta + f * 12, t);
-        tmem_ld4(ta + f * 12 + 4, t + 4);
-        tmem_ld4(ta + f * 12 + 8, t + 8);
-        tmem_ld_wait();
         if (a.dPO && n < a.N) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
             __stcs(a.dPO + ((size_t)n * 3 + c) * VP + v,
-                   __uint_as_float(t[c]) * dv[f][0] + __uint_as_float(t[4 + c]) * dv[f][1] + __uint_as_float(t[8 + c]) * dv[f][2]);
+                   __uint_as_float(t[f * 12 + c]) * dv[f][0] + __uint_as_float(t[f * 12 + 4 + c]) * dv[f][1] +
+                       __uint_as_float(t[f * 12 + 8 + c]) * dv[f][2]);
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty(b));
       // ---- G^T for the dA GEMM (the previous group's GEMM must have finished reading it)
       if (gi > 0) mbar_wait(gfree, (gi - 1) & 1);
 #pragma unroll
-      for (int f = 0; f < FB; ++f) {
+      for (int f = 0; f < FH; ++f) {
         const float ph[4] = {bs[0] + po[f][0], bs[1] + po[f][1], bs[2] + po[f][2], 1.f};
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -611,19 +604,18 @@ __global__ void __launch_bounds__(256, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
           for (int c = 0; c < 4; ++c) {
             float hi, lo;
             tf32_split(dv[f][r] * ph[c], hi, lo);
-            const uint32_t off = kmajor_sw128(f * 12 + r * 4 + c, lane);
-            *reinterpret_cast<float*>(gt + off) = hi;
-            *reinterpret_cast<float*>(gt + C_::GT_BYTES + off) = lo;
+            const uint32_t off = gt + kmajor_sw128((half * FH + f) * 12 + r * 4 + c, lane);
+            sts32(off, hi);
+            sts32(off + C_::GT_BYTES, lo);
           }
       }
       fence_proxy_async_smem();
       mbar_arrive(gfull);
 #pragma unroll
-      for (int f = 0; f < FB; ++f)
+      for (int f = 0; f < FH; ++f)
 #pragma unroll
         for (int c = 0; c < 3; ++c) { po[f][c] = pn[f][c]; dv[f][c] = dn[f][c]; }
-      sw[0] = swn[0];
-      sw[1] = swn[1];
+      sw = swn;
     }
   }
   tc_fence_before();
@@ -705,7 +697,7 @@ static int launch_bwd(const SkinBwdArgs& a, cudaStream_t s) {
     NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<NXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg::SMEM_BYTES));
     configured = true;
   }
-  k_skin_tc_bwd<NXR><<<NT_V * a.nchunks, 256, BwdCfg::SMEM_BYTES, s>>>(a);
+  k_skin_tc_bwd<NXR><<<NT_V * a.nchunks, 384, BwdCfg::SMEM_BYTES, s>>>(a);
   NB_LAUNCH_CHECK("skin_tc_bwd");
 }
 

@@ -10,6 +10,31 @@ namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Explicit shared-window accesses by 32-bit shared address.  The kernels carve their dynamic shared memory
+// through integer arithmetic (1024-byte alignment for the swizzled operand tiles), after which the compiler no
+// longer knows the address space and would emit generic LD / ST (slower path, tracked on the long scoreboard).
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -85,6 +110,12 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   d |= (uint64_t)layout << 61;
   return d;
+}
+// The start-address field is the low 14 bits, so stepping through a tile is a plain 64-bit add of
+// (byte offset >> 4): build the descriptor once, then advance it (the issuing thread is a single lane, every
+// instruction it spends on descriptor arithmetic delays the tensor pipe).
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t byte_off) {
+  return desc + (uint64_t)(byte_off >> 4);
 }
 // Instruction descriptor of tcgen05.mma.kind::tf32 with fp32 accumulation (dense, no negate).
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
