@@ -45,12 +45,68 @@ constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct GemmParams {
-  int M, N, K, ldc, act, ldg, accumulate, splits, mtiles, ntiles, kblocks, flush, hw_trunc;
+  int M, N, K, ldc, act, ldg, accumulate, splits, mtiles, ntiles, kblocks, flush, hw_trunc, vec;
   float gslope;
   const float* bias;
   const float* gate;
   float* C;
 };
+
+// Epilogue straight from the accumulator registers: this thread owns row m, 128 consecutive columns.
+// 16-byte vector stores (each lane its own row; consecutive instructions complete the 32-byte sectors in L2).
+// OUT 0 store, 1 read-add-store, 2 atomics (split-K).
+template <int OUT, bool HAS_GATE>
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, const float (&acc)[BN], size_t m, int ncol0, bool add_bias) {
+  float* crow = p.C + m * p.ldc + ncol0;
+  const float* grow = HAS_GATE ? p.gate + m * p.ldg + ncol0 : nullptr;
+#pragma unroll
+  for (int c4 = 0; c4 < BN / 4; ++c4) {
+    const int n = ncol0 + 4 * c4;
+    if (n >= p.N) break;  // uniform
+    float x[4] = {acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]};
+    const bool full = n + 3 < p.N;
+    if (add_bias) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] += (n + k < p.N) ? __ldg(p.bias + n + k) : 0.f;
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = fmaxf(x[k], 0.f);
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = x[k] > 0.f ? x[k] : 0.01f * x[k];
+    }
+    if (full) {
+      if (HAS_GATE) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(grow + 4 * c4));
+        x[0] *= g.x > 0.f ? 1.f : p.gslope; x[1] *= g.y > 0.f ? 1.f : p.gslope;
+        x[2] *= g.z > 0.f ? 1.f : p.gslope; x[3] *= g.w > 0.f ? 1.f : p.gslope;
+      }
+      float4* cp = reinterpret_cast<float4*>(crow + 4 * c4);
+      if (OUT == 2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(crow + 4 * c4 + k, x[k]);
+      } else if (OUT == 1) {
+        const float4 o = *cp;
+        *cp = make_float4(o.x + x[0], o.y + x[1], o.z + x[2], o.w + x[3]);
+      } else {
+        *cp = make_float4(x[0], x[1], x[2], x[3]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (n + k < p.N) {
+          float y = x[k];
+          if (HAS_GATE) y *= __ldg(grow + 4 * c4 + k) > 0.f ? 1.f : p.gslope;
+          float* cp = crow + 4 * c4 + k;
+          if (OUT == 2) atomicAdd(cp, y);
+          else if (OUT == 1) *cp += y;
+          else *cp = y;
+        }
+      }
+    }
+  }
+}
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
@@ -255,6 +311,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       }
       const int m_base = mb * BM + q * 32;
       if (m_base >= p.M) continue;  // warp-uniform
+      if (p.vec) {
+        if (m_base + lane < p.M) {
+          const size_t m = (size_t)(m_base + lane);
+          const bool ab = p.bias && split == 0;
+          if (p.gate) {
+            if (p.splits > 1) epilogue_row<2, true>(p, acc, m, nb * BN, ab);
+            else if (p.accumulate) epilogue_row<1, true>(p, acc, m, nb * BN, ab);
+            else epilogue_row<0, true>(p, acc, m, nb * BN, ab);
+          } else {
+            if (p.splits > 1) epilogue_row<2, false>(p, acc, m, nb * BN, ab);
+            else if (p.accumulate) epilogue_row<1, false>(p, acc, m, nb * BN, ab);
+            else epilogue_row<0, false>(p, acc, m, nb * BN, ab);
+          }
+        }
+        continue;
+      }
+      // C (or the gate) not 16-byte addressable: transpose through shared memory, coalesced scalar rows
       const int rows = min(32, p.M - m_base);
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
@@ -397,6 +470,7 @@ int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, 
   // tile serves as the hi part (NEMO_B200_GEMM_HWTRUNC=0 selects the explicit round-and-rewrite variant)
   static const int hw_trunc = [] { const char* e = getenv("NEMO_B200_GEMM_HWTRUNC"); return e ? atoi(e) : 1; }();
   p.hw_trunc = hw_trunc;
+  p.vec = (((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && (!gate || (((uintptr_t)gate & 15) == 0 && (ldg & 3) == 0))) ? 1 : 0;
   if (splits > 1 && !accumulate)
     NB_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
   CUtensorMap ta, tb;
