@@ -32,8 +32,16 @@ class ParamGroup:
     """One optimiser of the reference = one flat fp32 buffer (+ grad, Adam moments, device step count)."""
 
     def __init__(self, specs, device, lr, weight_decay=0.0, decoupled=False):
-        self.specs = specs                      # [(name, shape)]
-        n = sum(int(np.prod(s)) for _, s in specs)
+        """specs: [(name, shape)] or [(name, shape, ld)].  Every tensor starts on a 16-byte boundary and a matrix may
+        be stored with a padded row stride ld >= shape[1] (zero padding that Adam leaves at zero: zero gradient,
+        zero weight), which is what the TMA-fed GEMM needs; `views` are the logical (unpadded) tensors, `padded` /
+        `gpadded` the storage handed to the kernels."""
+        self.specs = [(sp[0], tuple(sp[1]), (sp[2] if len(sp) > 2 else (sp[1][-1] if len(sp[1]) else 1))) for sp in specs]
+        sizes = []
+        for _, shape, ld in self.specs:
+            k = int(np.prod(shape[:-1])) * ld if len(shape) >= 2 else int(np.prod(shape))
+            sizes.append((k + 3) // 4 * 4)
+        n = sum(sizes)
         self.p = torch.zeros(n, device=device)
         self.g = torch.zeros(n, device=device)
         self.m = torch.zeros(n, device=device)
@@ -41,14 +49,24 @@ class ParamGroup:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self.lr, self.wd, self.decoupled = float(lr), float(weight_decay), bool(decoupled)
         self.betas, self.eps = (0.9, 0.999), 1e-8
-        self.views, self.gviews, self.offsets = {}, {}, {}
+        self.views, self.gviews, self.offsets, self.padded, self.gpadded = {}, {}, {}, {}, {}
         o = 0
-        for name, shape in specs:
-            k = int(np.prod(shape))
-            self.views[name] = self.p[o:o + k].view(shape)
-            self.gviews[name] = self.g[o:o + k].view(shape)
+        for (name, shape, ld), size in zip(self.specs, sizes):
+            if len(shape) >= 2:
+                rows = int(np.prod(shape[:-1]))
+                k = rows * ld
+                self.padded[name] = self.p[o:o + k].view(rows, ld)
+                self.gpadded[name] = self.g[o:o + k].view(rows, ld)
+                self.views[name] = self.padded[name][:, :shape[-1]].view(*shape) if ld == shape[-1] \
+                    else self.padded[name][:, :shape[-1]]
+                self.gviews[name] = self.gpadded[name][:, :shape[-1]].view(*shape) if ld == shape[-1] \
+                    else self.gpadded[name][:, :shape[-1]]
+            else:
+                k = int(np.prod(shape))
+                self.views[name] = self.p[o:o + k].view(shape)
+                self.gviews[name] = self.g[o:o + k].view(shape)
             self.offsets[name] = (o, k)
-            o += k
+            o += size
 
     def adam_step(self):
         lib.increment(self.step_dev)
@@ -77,7 +95,9 @@ def fold_vposer(sd, device):
     Whf = Wh @ W7 @ W6f
     bhf = Wh @ (W7 @ b6f + b7) + bh
     f = lambda t: t.float().to(device).contiguous()
-    return dict(W1=f(W1f), b1=f(b1f), Wh=f(Whf), bh=f(bhf),
+    W1e = torch.zeros(W1f.shape[0], 72, dtype=torch.float64)
+    W1e[:, 3:66] = W1f
+    return dict(W1=f(W1f), W1e=f(W1e), b1=f(b1f), Wh=f(Whf), bh=f(bhf),
                 Wd0=f(g('decoder_net.0.weight')), bd0=f(g('decoder_net.0.bias')),
                 Wd3=f(g('decoder_net.3.weight')), bd3=f(g('decoder_net.3.bias')),
                 Wd5=f(g('decoder_net.5.weight')), bd5=f(g('decoder_net.5.bias')))
@@ -95,13 +115,14 @@ class FitEngine:
         self.Cc = int(a.instance_code_size)
         self.K = int(a.monotonic_network_n_nodes)
         self.in_dim = (self.D if self.D > 0 else 1) + self.Cc
+        self.ldx = (self.in_dim + 3) // 4 * 4      # row stride of X, dX and the first-layer weight
         self.basis = RBF_BASES.index(a.rbf_kernel) if self.D > 0 else 1
         self.focal = float(focal)
         self.IMG_D0, self.IMG_D1 = int(data['IMG_D0']), int(data['IMG_D1'])
         h, V, K = self.h, self.V, self.K
         # ---- parameters, grouped as the reference groups its optimisers
         self.g_cam = ParamGroup([('learned_cameras', (V, 9))], self.dev, a.lr_camera)
-        motion = [('learned_motion.net.net.0.weight', (h, self.in_dim)), ('learned_motion.net.net.0.bias', (h,)),
+        motion = [('learned_motion.net.net.0.weight', (h, self.in_dim), self.ldx), ('learned_motion.net.net.0.bias', (h,)),
                   ('learned_motion.net.net.2.weight', (h, h)), ('learned_motion.net.net.2.bias', (h,)),
                   ('learned_motion.net.net.4.weight', (h, h)), ('learned_motion.net.net.4.bias', (h,)),
                   ('learned_motion.rot_out.weight', (144, h)), ('learned_motion.linear_out.weight', (3, h)),
@@ -200,7 +221,7 @@ class FitEngine:
         z = lambda *s: torch.zeros(*s, device=d)
         nxr = self.ro['np'] + self.ro['nx']
         w = dict(
-            raw=z(N), X=z(Np, self.in_dim), warped=z(N), yn=z(self.V, 3),
+            raw=z(N), X=z(Np, self.ldx), warped=z(N), yn=z(self.V, 3),
             H1=z(Np, h), H2=z(Np, h), H3=z(Np, h), Y=z(Np, LDY),
             R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, LDF),
             PO_m=z(N, 3 * VP), PO_o=z(N, 3 * VP), PO_r=z(N, 3 * VP), dPO=z(N, 3 * VP),
@@ -211,7 +232,7 @@ class FitEngine:
             Rdec=z(N * 21, 9), recon=z(N, 69), signs=torch.zeros(N, 3, 2, VP // 32, dtype=torch.int32, device=d),
             ll=z(N), acc=z(8), terms=z(8), wts=z(8), total=z(1),
             d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
-            dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, LDY), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.in_dim),
+            dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, LDY), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.ldx),
             dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dbase=z(3 * VP),
             base=z(3, VP), J=z(72), vi=torch.zeros(N, dtype=torch.long, device=d),
             fi=torch.zeros(N, dtype=torch.long, device=d), noise=z(N, max(self.Cc, 1)),
@@ -236,10 +257,11 @@ class FitEngine:
             noise = w['noise']
         lib.embed_fwd(raw_phase, view_idx, gp['shifts'], gp['scales'], self.K, self.centres,
                       mv['phase_rbf.log_sigmas'] if self.D > 0 else None, self.D, self.basis, codes, C, noise,
-                      w['X'], self.in_dim, w['warped'], w['yn'], N, self.V)
+                      w['X'], self.ldx, w['warped'], w['yn'], N, self.V)
         W = lambda i: mv['learned_motion.net.net.%d.weight' % i]
         b = lambda i: mv['learned_motion.net.net.%d.bias' % i]
-        gemm(w['X'], W(0), w['H1'], Np, h, self.in_dim, self.in_dim, self.in_dim, h, transB=True, bias=b(0), act=1)
+        gemm(w['X'], self.g_motion.padded['learned_motion.net.net.0.weight'], w['H1'], Np, h, self.in_dim, self.ldx,
+             self.ldx, h, transB=True, bias=b(0), act=1)
         gemm(w['H1'], W(2), w['H2'], Np, h, h, h, h, h, transB=True, bias=b(2), act=1)
         # FCNN's last Linear followed by MotionNet.relu (:132)
         gemm(w['H2'], W(4), w['H3'], Np, h, h, h, h, h, transB=True, bias=b(4), act=1)
@@ -301,7 +323,9 @@ class FitEngine:
         if full:
             vp = self.vp
             # VPoser encode (mean) -> decode (:2779-2784)
-            gemm(w['aa'].view(-1)[3:], vp['W1'], w['E1'], N, H_VP, 63, 72, 63, H_VP, transB=True, bias=vp['b1'], act=2)
+            # W1e is the folded first encoder layer widened to all 72 axis-angle columns (zero columns for the global
+            # orientation and the two hand joints), so the GEMM reads the 16-byte aligned (N,72) buffer directly
+            gemm(w['aa'], vp['W1e'], w['E1'], N, H_VP, 72, 72, 72, H_VP, transB=True, bias=vp['b1'], act=2)
             gemm(w['E1'], vp['Wh'], w['head'], N, 2 * L_VP, H_VP, H_VP, H_VP, 2 * L_VP, transB=True, bias=vp['bh'])
             lib.vposer_kl(w['head'], L_VP, None, acc[1:2], ls * w_kl / N, w['dhead'], N)
             gemm(w['head'], vp['Wd0'], w['D1'], N, H_VP, L_VP, 2 * L_VP, L_VP, H_VP, transB=True, bias=vp['bd0'], act=2)
@@ -364,7 +388,7 @@ class FitEngine:
                 vp = self.vp
                 gemm(w['dhead'], vp['Wh'], w['dE1'], N, H_VP, 2 * L_VP, 2 * L_VP, H_VP, H_VP, gate=w['E1'], ldg=H_VP,
                      gate_slope=0.01)
-                gemm(w['dE1'], vp['W1'], w['d_aa'].view(-1)[3:], N, 63, H_VP, H_VP, 63, 72, accumulate=True)
+                gemm(w['dE1'], vp['W1e'], w['d_aa'], N, 72, H_VP, H_VP, 72, 72, accumulate=True)
             if full and w_vp:
                 lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, C.W2, None, 0, None, 0, None, None, w['signs'],
                              ls * w_vp / (N * NV * 3.0), w['dPO'], w['dA'], N)
@@ -429,13 +453,15 @@ class FitEngine:
         gemm(w['dHb'], w['H1'], gW(2), h, h, Np, h, h, h, transA=True)
         lib.colsum(w['dHb'], gb(2), Np, h, h, 0)
         gemm(w['dHb'], W(2), w['dHa'], Np, h, h, h, h, h, gate=w['H1'], ldg=h)
-        gemm(w['dHa'], w['X'], gW(0), h, ind, Np, h, ind, ind, transA=True)
+        gemm(w['dHa'], w['X'], self.g_motion.gpadded['learned_motion.net.net.0.weight'], h, ind, Np, h, self.ldx,
+             self.ldx, transA=True)
         lib.colsum(w['dHa'], gb(0), Np, h, h, 0)
-        gemm(w['dHa'], W(0), w['dX'], Np, ind, h, h, ind, ind)
+        gemm(w['dHa'], self.g_motion.padded['learned_motion.net.net.0.weight'], w['dX'], Np, ind, h, h, self.ldx,
+             self.ldx)
         gp, gg = self.g_phase.views, self.g_phase.gviews
         lib.embed_bwd(w['raw'], vi, gp['shifts'], gp['scales'], self.K, self.centres,
                       mv['phase_rbf.log_sigmas'] if self.D > 0 else None, self.D, self.basis, self.Cc, w['warped'],
-                      w['yn'], w['dX'], ind, gv['phase_rbf.log_sigmas'] if self.D > 0 else None, gg['shifts'],
+                      w['yn'], w['dX'], self.ldx, gv['phase_rbf.log_sigmas'] if self.D > 0 else None, gg['shifts'],
                       gg['scales'], self.g_inst.gviews['learned_instance_code'] if self.g_inst else None, w['gy01'], N,
                       self.V)
 
