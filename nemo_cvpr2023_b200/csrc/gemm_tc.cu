@@ -3,19 +3,23 @@
 // 130-148), VPoser (human_body_prior/models/vposer_model.py:63-88), the pose-blend matmul (lbs.py:229-233)
 // and their autograd backward (dgrad / wgrad).
 //
-// Persistent, warp-specialised kernel, one CTA per SM, 128 x 128 x 32 tiles:
-//   warp 0      TMA producer     cp.async.bulk.tensor of the raw fp32 A / B boxes into a 4-deep ring
-//   warps 2-3   converters       split every fp32 of the stage into tf32 hi (in place) + lo (2-deep side ring)
-//   warp 1      MMA issuer       per 8-wide k step: lo.hi + hi.lo + hi.hi via tcgen05.mma.kind::tf32 into a TMEM
-//                                partial accumulator (2 x 128 columns, double buffered)
-//   warps 4-7   accumulate +     tcgen05.ld the partial every `flush` k-blocks and add it into fp32 registers
-//               epilogue         (round-to-nearest): the tensor core accumulates with truncation, so long chains
-//                                in TMEM would cost ~K/8 * 3 * 2^-24 relative; short chains keep fp32 accuracy
-//                                for K = 20736.  Then transpose through shared memory -> bias / activation /
-//                                gate / accumulate -> coalesced 128-byte row stores (atomics under split-K).
-// Both operands may be K-major (K contiguous; 128-byte swizzle) or MN-major (M/N contiguous; 128-byte swizzle
-// with 32-byte atoms, the only MN-major layout tf32 operands support), so NN / NT / TN / TT all run without
-// a transpose pass.  M, N, K tails are handled by TMA zero fill and predicated stores.
+// Persistent, warp-specialised kernel, one CTA (512 threads) per SM, 128 x 128 x 32 tiles:
+//   warp 0       TMA producer    cp.async.bulk.tensor of the raw fp32 A / B boxes into a 4-deep shared-memory ring
+//   warps 4-7    A converters    thread = tile row: read the row's 32 k values from the (swizzled) raw tile, split
+//                                into tf32 hi / lo and tcgen05.st both into TENSOR MEMORY: the A operand of the
+//                                MMAs comes from TMEM, which removes its shared-memory operand traffic (with both
+//                                operands in shared memory a 128 x 128 x 8 MMA is fetch-bound at ~50 % of the pipe)
+//   warps 2-3    B converters    write lo = x - trunc_tf32(x) into a 2-deep side ring; the raw tile is the hi operand
+//                                (the tensor core ignores the low 13 mantissa bits; measured)
+//   warp 1       MMA issuer      per 8-wide k step: lo.hi + hi.lo + hi.hi via tcgen05.mma.kind::tf32 (A from TMEM, B
+//                                by shared-memory descriptor) into a TMEM partial (2 x 128 columns, double buffered)
+//   warps 8-15   accumulate +    tcgen05.ld the partial every `flush` k-blocks and add it into fp32 registers
+//                epilogue        (round-to-nearest; the tensor core accumulates with truncation, ~K/8*3*2^-24
+//                                relative on long chains), 64 columns per warp; then bias / activation / gate /
+//                                accumulate and 16-byte vector stores straight from registers (atomics under split-K)
+// A may be K-major (128-byte swizzle) or MN-major (128-byte swizzle with 32-byte atoms; un-transposed by the
+// converters), B K-major or MN-major (the only MN-major layout tf32 operands support), so NN / NT / TN / TT all
+// run without a transpose pass.  M, N, K tails are handled by TMA zero fill and predicated stores.
 #include <stdlib.h>
 #include <cuda.h>  // CUtensorMap types; the driver entry point is fetched at run time (no libcuda link)
 #include <map>
@@ -30,37 +34,42 @@ using namespace nb::sm100;
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32, UMMA_K = 8;
-constexpr int NUM_THREADS = 256;   // 8 warps -> up to 255 registers per thread for the accumulate warps
-constexpr int CONV_THREADS = 64;
-constexpr int A_BYTES = BM * BK * 4;  // 16 KB
-constexpr int B_BYTES = BN * BK * 4;  // 16 KB
+constexpr int NUM_THREADS = 512;
+constexpr int BCONV_THREADS = 64, ACONV_THREADS = 128, ACC_THREADS = 256;
+constexpr int NC = BN / 2;                         // accumulator columns per epilogue thread
+constexpr int A_BYTES = BM * BK * 4;               // 16 KB
+constexpr int B_BYTES = BN * BK * 4;               // 16 KB
 constexpr int RAW_STAGES = 4, LO_STAGES = 2;
-constexpr int RAW_BYTES = A_BYTES + B_BYTES;       // [A raw -> hi][B raw -> hi]
-constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;     // one padded 32x32 transpose tile per epilogue warp
-constexpr int OFF_LO = RAW_STAGES * RAW_BYTES;
-constexpr int OFF_STAGING = OFF_LO + LO_STAGES * RAW_BYTES;
+constexpr int RAW_BYTES = A_BYTES + B_BYTES;       // [A raw][B raw = hi operand]
+constexpr int STAGING_BYTES = 8 * 32 * 33 * 4;     // one padded 32x32 transpose tile per epilogue warp
+constexpr int OFF_LO = RAW_STAGES * RAW_BYTES;     // B lo ring
+constexpr int OFF_STAGING = OFF_LO + LO_STAGES * B_BYTES;
 constexpr int OFF_BARS = OFF_STAGING + STAGING_BYTES;
-constexpr int TMEM_COLS = 2 * BN;
+constexpr int TMEM_COLS = 512;                     // partials 2 x 128 | A stages 4 x (32 hi + 32 lo)
+constexpr int TMEM_A = 2 * BN;
 constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TMEM_A + RAW_STAGES * 2 * BK <= TMEM_COLS, "tensor memory budget");
 
 struct GemmParams {
-  int M, N, K, ldc, act, ldg, accumulate, splits, mtiles, ntiles, kblocks, flush, hw_trunc, vec;
+  int M, N, K, ldc, act, ldg, accumulate, splits, mtiles, ntiles, kblocks, flush, vec;
   float gslope;
   const float* bias;
   const float* gate;
   float* C;
 };
 
-// Epilogue straight from the accumulator registers: this thread owns row m, 128 consecutive columns.
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Epilogue straight from the accumulator registers: this thread owns row m, NC consecutive columns from ncol0.
 // 16-byte vector stores (each lane its own row; consecutive instructions complete the 32-byte sectors in L2).
 // OUT 0 store, 1 read-add-store, 2 atomics (split-K).
 template <int OUT, bool HAS_GATE>
-__device__ __forceinline__ void epilogue_row(const GemmParams& p, const float (&acc)[BN], size_t m, int ncol0, bool add_bias) {
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, const float (&acc)[NC], size_t m, int ncol0, bool add_bias) {
   float* crow = p.C + m * p.ldc + ncol0;
   const float* grow = HAS_GATE ? p.gate + m * p.ldg + ncol0 : nullptr;
 #pragma unroll
-  for (int c4 = 0; c4 < BN / 4; ++c4) {
+  for (int c4 = 0; c4 < NC / 4; ++c4) {
     const int n = ncol0 + 4 * c4;
     if (n >= p.N) break;  // uniform
     float x[4] = {acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]};
@@ -113,15 +122,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                                                             const __grid_constant__ CUtensorMap tmB,
                                                             const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sbase = smem_u32(smem);
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = sbase + OFF_BARS;
-  auto full = [&](int s) { return bars + 8u * s; };                          // TMA landed        (tx)
-  auto conv = [&](int s) { return bars + 8u * (RAW_STAGES + s); };           // hi/lo written     (64)
-  auto empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };      // MMAs read raw/hi  (commit)
-  auto loempty = [&](int l) { return bars + 8u * (3 * RAW_STAGES + l); };    // MMAs read lo      (commit)
-  auto pfull = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 2 + b); };  // partial complete  (commit)
-  auto pempty = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 4 + b); }; // partial drained   (128)
+  auto full = [&](int s) { return bars + 8u * s; };                          // TMA landed            (tx)
+  auto conv = [&](int s) { return bars + 8u * (RAW_STAGES + s); };           // A in TMEM, B lo ready (192)
+  auto empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };      // MMAs done with stage  (commit)
+  auto loempty = [&](int l) { return bars + 8u * (3 * RAW_STAGES + l); };    // MMAs done with B lo   (commit)
+  auto pfull = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 2 + b); };  // partial complete      (commit)
+  auto pempty = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 4 + b); }; // partial drained       (256)
   const uint32_t tmem_slot = bars + 8u * (3 * RAW_STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,13 +138,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < RAW_STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(conv(s), CONV_THREADS);
+      mbar_init(conv(s), ACONV_THREADS + BCONV_THREADS);
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(loempty(b), 1);
       mbar_init(pfull(b), 1);
-      mbar_init(pempty(b), 128);
+      mbar_init(pempty(b), ACC_THREADS);
     }
     fence_barrier_init();
   }
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   const uint32_t tmem_base = lds32u(tmem_slot);
 
   const int units = p.mtiles * p.ntiles * p.splits;
-  constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, B_MN ? 1 : 0);  // A is K-major in TMEM whatever its source
   auto krange = [&](int split, int& kb0, int& kb1) {
     kb0 = (int)((long long)split * p.kblocks / p.splits);
     kb1 = (int)((long long)(split + 1) * p.kblocks / p.splits);
@@ -164,8 +172,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
         krange(split, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % RAW_STAGES;
-          const uint32_t ph = (it / RAW_STAGES) & 1;
-          mbar_wait(empty(s), ph ^ 1);
+          mbar_wait(empty(s), ((it / RAW_STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(full(s), RAW_BYTES);
           const uint32_t sa = sbase + s * RAW_BYTES, sb = sa + A_BYTES;
           if (!A_MN) {
@@ -201,24 +208,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             const int s = it % RAW_STAGES, l = it % LO_STAGES;
             mbar_wait(conv(s), (it / RAW_STAGES) & 1);
             tc_fence_after();
-            const uint32_t a_hi = sbase + s * RAW_BYTES, b_hi = a_hi + A_BYTES;
-            const uint32_t a_lo = sbase + OFF_LO + l * RAW_BYTES, b_lo = a_lo + A_BYTES;
-            const uint64_t ah0 = A_MN ? umma_smem_desc(a_hi, BK * 128, 512, LAYOUT_SW128_BASE32B)
-                                      : umma_smem_desc(a_hi, 16, 1024, LAYOUT_SW128);
+            const uint32_t a_hi = tmem_base + TMEM_A + s * (2 * BK), a_lo = a_hi + BK;
+            const uint32_t b_hi = sbase + s * RAW_BYTES + A_BYTES, b_lo = sbase + OFF_LO + l * B_BYTES;
             const uint64_t bh0 = B_MN ? umma_smem_desc(b_hi, BK * 128, 512, LAYOUT_SW128_BASE32B)
                                       : umma_smem_desc(b_hi, 16, 1024, LAYOUT_SW128);
-            const uint64_t al0 = umma_desc_advance(ah0, a_lo - a_hi), bl0 = umma_desc_advance(bh0, b_lo - b_hi);
+            const uint64_t bl0 = B_MN ? umma_smem_desc(b_lo, BK * 128, 512, LAYOUT_SW128_BASE32B)
+                                      : umma_smem_desc(b_lo, 16, 1024, LAYOUT_SW128);
 #pragma unroll
             for (int j = 0; j < BK / UMMA_K; ++j) {
-              constexpr uint32_t ASTEP = A_MN ? UMMA_K * 128 : UMMA_K * 4, BSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 4;
-              const uint64_t ah = umma_desc_advance(ah0, j * ASTEP), al = umma_desc_advance(al0, j * ASTEP);
+              constexpr uint32_t BSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 4;
               const uint64_t bh = umma_desc_advance(bh0, j * BSTEP), bl = umma_desc_advance(bl0, j * BSTEP);
-              umma_tf32(d, al, bh, idesc, (kb > kc || j > 0) ? 1u : 0u);
-              umma_tf32(d, ah, bl, idesc, 1u);
-              umma_tf32(d, ah, bh, idesc, 1u);
+              umma_tf32_ts(d, a_lo + j * UMMA_K, bh, idesc, (kb > kc || j > 0) ? 1u : 0u);
+              umma_tf32_ts(d, a_hi + j * UMMA_K, bl, idesc, 1u);
+              umma_tf32_ts(d, a_hi + j * UMMA_K, bh, idesc, 1u);
             }
-            umma_commit(empty(s));    // raw/hi stage reusable once these MMAs have read it
-            umma_commit(loempty(l));  // and so is the lo slot
+            umma_commit(empty(s));    // raw stage (and its TMEM A slot) reusable once these MMAs have completed
+            umma_commit(loempty(l));  // and so is the B lo slot
           }
           umma_commit(pfull(pb));  // partial accumulator complete
         }
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
     }
     __syncwarp();
   } else if (warp < 4) {
-    // ------------------------------------------------------------------ converters (64 threads)
+    // ------------------------------------------------------------------ B converters (64 threads)
     const int ct = threadIdx.x - 64;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -234,71 +239,92 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       krange(u % p.splits, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % RAW_STAGES, l = it % LO_STAGES;
-        const uint32_t hi = sbase + s * RAW_BYTES + 16 * ct, lo = sbase + OFF_LO + l * RAW_BYTES + 16 * ct;
-        constexpr uint32_t CS = 16 * CONV_THREADS;
+        const uint32_t hi = sbase + s * RAW_BYTES + A_BYTES + 16 * ct, lo = sbase + OFF_LO + l * B_BYTES + 16 * ct;
+        constexpr uint32_t CS = 16 * BCONV_THREADS;
         mbar_wait(loempty(l), ((it / LO_STAGES) & 1) ^ 1);
         mbar_wait(full(s), (it / RAW_STAGES) & 1);
-        // software pipelined over batches of 8 independent 16-byte loads: the next batch is in flight while the
-        // current one is split and stored (hi and lo alias as far as the compiler knows, so a plain
-        // load-split-store loop would serialise on shared-memory latency)
-        constexpr int NB8 = RAW_BYTES / 16 / CONV_THREADS / 8;
-        float4 x[8], y[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = lds128(hi + CS * j);
+        constexpr int NB8 = B_BYTES / 16 / BCONV_THREADS / 8;
 #pragma unroll
         for (int bt = 0; bt < NB8; ++bt) {
-          if (bt + 1 < NB8) {
+          float4 x[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = lds128(hi + CS * (8 * (bt + 1) + j));
+          for (int j = 0; j < 8; ++j) x[j] = lds128(hi + CS * (8 * bt + j));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 w;
+            w.x = x[j].x - trunc_tf32(x[j].x); w.y = x[j].y - trunc_tf32(x[j].y);
+            w.z = x[j].z - trunc_tf32(x[j].z); w.w = x[j].w - trunc_tf32(x[j].w);
+            sts128(lo + CS * (8 * bt + j), w);
           }
-          if (p.hw_trunc) {
-            // the tensor core ignores the low 13 mantissa bits of a tf32 operand: the raw fp32 tile is the hi
-            // operand as it stands, only lo = x - trunc(x) is written
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 w;
-              w.x = x[j].x - __uint_as_float(__float_as_uint(x[j].x) & 0xffffe000u);
-              w.y = x[j].y - __uint_as_float(__float_as_uint(x[j].y) & 0xffffe000u);
-              w.z = x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xffffe000u);
-              w.w = x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xffffe000u);
-              sts128(lo + CS * (8 * bt + j), w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 h, w;
-              tf32_split4(x[j], h, w);
-              sts128(hi + CS * (8 * bt + j), h);
-              sts128(lo + CS * (8 * bt + j), w);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = y[j];
         }
         fence_proxy_async_smem();
         mbar_arrive(conv(s));
       }
     }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ A converters (128 threads, thread = row)
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int kb0, kb1;
+      krange(u % p.splits, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % RAW_STAGES;
+        const uint32_t sa = sbase + s * RAW_BYTES;
+        mbar_wait(full(s), (it / RAW_STAGES) & 1);
+        uint32_t h[32], w[32];
+        if (!A_MN) {
+          // K-major raw tile: row r = 128 bytes, 16-byte chunk c stored at chunk (c ^ (r & 7))
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = lds128(sa + row * 128 + ((c ^ (row & 7)) << 4));
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float t = trunc_tf32(xs[e]);
+              h[4 * c + e] = __float_as_uint(t);
+              w[4 * c + e] = __float_as_uint(xs[e] - t);
+            }
+          }
+        } else {
+          // MN-major raw tile: [m-block q][k row = 128 bytes of 32 m], 32-byte chunk j stored at chunk (j ^ (k & 3))
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = lds32(sa + q * (BK * 128) + k * 128 + ((((lane >> 3) ^ k) & 3) << 5) + ((lane & 7) << 2));
+            const float t = trunc_tf32(x);
+            h[k] = __float_as_uint(t);
+            w[k] = __float_as_uint(x - t);
+          }
+        }
+        // the TMEM slot of this stage was released together with the shared-memory stage (empty -> TMA -> full)
+        tmem_st32(trow + s * (2 * BK), h);
+        tmem_st32(trow + s * (2 * BK) + BK, w);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(conv(s));
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ accumulate + epilogue (128 threads)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const uint32_t st = sbase + OFF_STAGING + q * (32 * 33 * 4);
+    // ------------------------------------------------------------------ accumulate + epilogue (256 threads)
+    const int q = warp & 3, hc = (warp - 8) >> 2;  // TMEM lane quarter, column half
+    const uint32_t st = sbase + OFF_STAGING + (warp - 8) * (32 * 33 * 4);
     uint32_t pc = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int split = u % p.splits, tile = u / p.splits;
       const int mb = tile % p.mtiles, nb = tile / p.mtiles;
       int kb0, kb1;
       krange(split, kb0, kb1);
-      float acc[BN];
+      float acc[NC];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int j = 0; j < NC; ++j) acc[j] = 0.f;
       for (int kc = kb0; kc < kb1; kc += p.flush, ++pc) {
         const uint32_t pb = pc & 1, pph = (pc >> 1) & 1;
         mbar_wait(pfull(pb), pph);
         tc_fence_after();
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + pb * BN;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + pb * BN + hc * NC;
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < NC / 32; ++c) {
           uint32_t v[32];
           tmem_ld16(ta + c * 32, v);
           tmem_ld16(ta + c * 32 + 16, v + 16);
@@ -311,18 +337,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       }
       const int m_base = mb * BM + q * 32;
       if (m_base >= p.M) continue;  // warp-uniform
+      const int ncol0 = nb * BN + hc * NC;
+      if (ncol0 >= p.N) continue;
       if (p.vec) {
         if (m_base + lane < p.M) {
           const size_t m = (size_t)(m_base + lane);
           const bool ab = p.bias && split == 0;
           if (p.gate) {
-            if (p.splits > 1) epilogue_row<2, true>(p, acc, m, nb * BN, ab);
-            else if (p.accumulate) epilogue_row<1, true>(p, acc, m, nb * BN, ab);
-            else epilogue_row<0, true>(p, acc, m, nb * BN, ab);
+            if (p.splits > 1) epilogue_row<2, true>(p, acc, m, ncol0, ab);
+            else if (p.accumulate) epilogue_row<1, true>(p, acc, m, ncol0, ab);
+            else epilogue_row<0, true>(p, acc, m, ncol0, ab);
           } else {
-            if (p.splits > 1) epilogue_row<2, false>(p, acc, m, nb * BN, ab);
-            else if (p.accumulate) epilogue_row<1, false>(p, acc, m, nb * BN, ab);
-            else epilogue_row<0, false>(p, acc, m, nb * BN, ab);
+            if (p.splits > 1) epilogue_row<2, false>(p, acc, m, ncol0, ab);
+            else if (p.accumulate) epilogue_row<1, false>(p, acc, m, ncol0, ab);
+            else epilogue_row<0, false>(p, acc, m, ncol0, ab);
           }
         }
         continue;
@@ -330,8 +358,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       // C (or the gate) not 16-byte addressable: transpose through shared memory, coalesced scalar rows
       const int rows = min(32, p.M - m_base);
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = nb * BN + c * 32;
+      for (int c = 0; c < NC / 32; ++c) {
+        const int n0 = ncol0 + c * 32;
         if (n0 < p.N) {  // warp-uniform
 #pragma unroll
           for (int j = 0; j < 32; ++j) sts32(st + 4 * (lane * 33 + j), acc[c * 32 + j]);
@@ -464,12 +492,10 @@ int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, 
   if (force_splits > 0) splits = (act == 0) ? min(force_splits, p.kblocks) : 1;
   p.splits = splits;
   // k-blocks accumulated in TMEM before the partial is folded into the fp32 registers: short reductions go in
-  // one piece (the epilogue then overlaps the next tile), deep ones in chains of 2 x 12 MMAs
-  p.flush = (cdiv(p.kblocks, splits) <= 8) ? 8 : 2;
-  // measured on B200: tcgen05.mma.kind::tf32 ignores the low 13 mantissa bits of its operands, so the raw fp32
-  // tile serves as the hi part (NEMO_B200_GEMM_HWTRUNC=0 selects the explicit round-and-rewrite variant)
-  static const int hw_trunc = [] { const char* e = getenv("NEMO_B200_GEMM_HWTRUNC"); return e ? atoi(e) : 1; }();
-  p.hw_trunc = hw_trunc;
+  // one piece (the epilogue then overlaps the next tile), deep ones in chains of 4 x 12 MMAs
+  { const int kpu = cdiv(p.kblocks, splits); p.flush = kpu <= 8 ? 8 : (kpu <= 64 ? 2 : 4); }
+  static const int flush_env = [] { const char* e = getenv("NEMO_B200_GEMM_FLUSH"); return e ? atoi(e) : 0; }();
+  if (flush_env > 0) p.flush = flush_env;   // experiment knob: k-blocks per TMEM partial
   p.vec = (((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && (!gate || (((uintptr_t)gate & 15) == 0 && (ldg & 3) == 0))) ? 1 : 0;
   if (splits > 1 && !accumulate)
     NB_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
