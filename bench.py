@@ -11,6 +11,7 @@ Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every fi
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -48,36 +49,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms by one long-running `nvidia-smi -lms`, started
+    before warm-up; only samples that fall inside a timed `window()` count (the GPU is under load there)."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
-        self.rows, self.stop, self.index = [], False, index
+        self.rows, self.windows, self.index, self.proc = [], [], index, None
 
     def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(',')])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.strip().split(',')]))
 
-    def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
         return self
 
-    def __exit__(self, *a):
-        self.stop = True
-        self.t.join(timeout=6)
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=5)
+            self.proc = None
+
+    @contextlib.contextmanager
+    def window(self):
+        t0 = time.perf_counter()
+        try:
+            yield self
+        finally:
+            self.windows.append((t0, time.perf_counter()))
 
     def summary(self):
-        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 6 and r[0].isdigit()
+                and any(a <= t <= b for a, b in self.windows)]
         if not rows:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in rows)]
         return {'sm_mhz': float(np.median([float(r[0]) for r in rows])), 'sm_max_mhz': float(rows[0][1]),
@@ -154,17 +171,14 @@ def k7_roofline(dev, iters=10):
     A = torch.randn(N, 24, 12, device=dev, generator=g)
     PO = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
     dV = torch.randn(N, Fn.NV, 3, device=dev, generator=g)
-    ro = C.readout
-    dJX = torch.randn(N, ro['np'] + ro['nx'], 3, device=dev, generator=g)
     Vout = torch.empty(N, Fn.NV, 3, device=dev)
-    JX = torch.empty(N, ro['np'] + ro['nx'], 3, device=dev)
-    dPO, dA = torch.empty_like(PO), torch.empty(N, 24, 12, device=dev)
+    dPO, dAt = torch.empty_like(PO), torch.empty(N, 12, 24, device=dev)
 
     def fwd():
-        lib.skin_fwd(A, PO, C.vt, C.Wt, ro['Jx'], ro['nx'], ro['slot'], ro['np'], Vout, JX, N)
+        lib.skin_fwd(A, PO, C.vt, C.Wt, Vout, N)
 
     def bwd():
-        lib.skin_bwd(A, PO, C.vt, C.Wt, C.W2, ro['Jx'], ro['nx'], ro['slot'], ro['np'], dV, dJX, None, 0.0, dPO, dA, N)
+        lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAt, N)
 
     out = {}
     for name, fn in (('fwd', fwd), ('bwd', bwd)):
@@ -237,23 +251,28 @@ def run_gpu(a):
     def e2e_step():      # the public call: pinned host indices in, loss dict out
         model.step(vi_h, fi_h)
 
+    cs = ClockSampler(local).start()
     for _ in range(max(3, a.warmup)):
         dev_step()
-    with ClockSampler(local) as cs:
+    with cs.window():
         l0 = lib.launches
         t_dev = timed(dev_step, a.steps)
         launches = (lib.launches - l0) // a.steps
-    clocks = cs.summary()
     for _ in range(2):
         e2e_step()
-    t_e2e = timed(e2e_step, a.steps)
+    with cs.window():
+        t_e2e = timed(e2e_step, a.steps)
     if rank != 0:
+        cs.stop()
         return
     total = N * world
     value = total * a.steps / t_dev
     e2e_val = total * a.steps / t_e2e
     peak, peak_src = peaks()
-    nK7, tk = k7_roofline(dev)
+    with cs.window():
+        nK7, tk = k7_roofline(dev)
+    cs.stop()
+    clocks = cs.summary()
     alg = 5 * STREAM_BYTES * nK7
     achieved = alg / (tk['fwd'] + tk['bwd']) / 1e9
     cpu_fps, cpu_med, cores = time_cpu(3, 1)
@@ -264,7 +283,7 @@ def run_gpu(a):
         'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': int(2 * N * 8),
                 'd2h_bytes_per_step': 9 * 4, 'ms_per_step': t_e2e / a.steps * 1e3},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': 'k_skin_fwd + k_skin_bwd (K7, vertices written, dV read: 5 streams/frame)',
+        'roofline': {'bound': 'hbm', 'kernel': 'k_skin_tc_fwd<0> + k_skin_tc_bwd<dV> (K7, vertices written, dV read: 5 streams/frame)',
                      'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': None,
                      'algorithmic_bytes_per_launch_pair': alg, 'fwd_ms': tk['fwd'] * 1e3, 'bwd_ms': tk['bwd'] * 1e3,

@@ -95,31 +95,28 @@ int nemo_b200_pose_feature(const float* R, float* F, int ldf, int N, void* strea
  * out: A (N,24,12) relative 3x4 transforms, JP (N,24,3) posed joints. */
 int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride, const int* parents,
                         float* A, float* JP, int N, void* stream);
-/* dR (N,24,9) overwritten; dJ (N,24,3) overwritten when j_stride != 0, else (24,3) ACCUMULATED
- * with atomics (caller zeroes). */
+/* dA (N,24,12) and dAt (N,12,24) (the same gradient transposed, as nemo_b200_skin_bwd reduces it) are summed;
+ * either may be NULL.  dR (N,24,9) overwritten; dJ (N,24,3) overwritten when j_stride != 0, else (24,3)
+ * ACCUMULATED with atomics (caller zeroes). */
 int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents,
-                        const float* dA, const float* dJP, float* dR, float* dJ, int N, void* stream);
+                        const float* dA, const float* dAt, const float* dJP, float* dR, float* dJ, int N,
+                        void* stream);
 
 /* ---------------------------------------------------------------- skinning (K7)
- * lbs.py:236-252 (v_posed, T = W.A, v = T.[v_posed;1]) + the joint read-outs of smplx
- * VertexJointSelector and hmr/smpl.py:33-36 (J_regressor_extra), fused; no per-vertex
- * intermediate is written.  v_posed[n] = base + PO[n] (PO may be NULL).
+ * lbs.py:236-252 (v_posed, T = W.A, v = T.[v_posed;1]), fused; no per-vertex intermediate is written.
+ * v_posed[n] = base + PO[n].
  *   A    (N,24,12)           PO   (N,3,VP) planar      base (3,VP) planar
  *   Wt   (24,VP) transposed skinning weights, zero padded
- *   W2   (VP,8,4) the same weights grouped 3 joints per float4 (4th lane 0), for the dA reduction
- *   Jx   (nx,VP) extra joint regressor rows, zero padded (nx <= 10)
- *   slot int8[VP]: index of the vertex in the pick list (np <= 22 unique ids) or -1
- * out: V (N,6890,3) interleaved or NULL;  JX (N,np+nx,3): picked vertices then regressed joints. */
+ * out: V (N,6890,3) interleaved (the reference layout). */
 int nemo_b200_skin_fwd(const float* A, const float* PO, const float* base, const float* Wt,
-                       const float* Jx, int nx, const signed char* slot, int np,
-                       float* V, float* JX, int N, void* stream);
+                       float* V, int N, void* stream);
 /* backward.  Upstream gradient of the vertices = dV (N,6890,3) [may be NULL]
- *   + the read-outs' dJX (N,np+nx,3) [may be NULL] + sign_scale * sign bits [signs may be NULL].
- * out: dPO (N,3,VP) overwritten (may be NULL), dA (N,24,12) overwritten.  d base = column sum of dPO. */
-int nemo_b200_skin_bwd(const float* A, const float* PO, const float* base, const float* Wt, const float* W2,
-                       const float* Jx, int nx, const signed char* slot, int np,
-                       const float* dV, const float* dJX, const uint32_t* signs, float sign_scale,
-                       float* dPO, float* dA, int N, void* stream);
+ *   + sign_scale * sign bits [signs may be NULL]; at least one of the two.
+ * out: dPO (N,3,VP) overwritten, dAt (N,12,24) overwritten (TRANSPOSED per frame: dAt[n][r*4+c][j];
+ * nemo_b200_chain_bwd consumes it as is).  d base = column sum of dPO. */
+int nemo_b200_skin_bwd(const float* A, const float* PO, const float* base, const float* Wt,
+                       const float* dV, const uint32_t* signs, float sign_scale,
+                       float* dPO, float* dAt, int N, void* stream);
 /* fused vertex-to-vertex L1 of MultiViewModel.vposer_loss (nemo/neural_motion_model.py:2792-2797):
  * l1_sum[0] += sum_{n,v,c} | v_b - v_a |  (mesh a = "orig", carries the gradient; mesh b = detached
  * reconstruction).  signs (N,3,2,VP/32) uint32 receives the (v_a > v_b, v_a < v_b) bit masks that
@@ -127,6 +124,23 @@ int nemo_b200_skin_bwd(const float* A, const float* PO, const float* base, const
 int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const float* A_b, const float* PO_b,
                           const float* base, const float* Wt, uint32_t* signs, float* l1_sum, int N,
                           void* stream);
+
+/* ---------------------------------------------------------------- joint read-outs (K7j)
+ * smplx VertexJointSelector (picked vertices) and hmr/smpl.py:33-36 (J_regressor_extra . vertices),
+ * evaluated WITHOUT the mesh: a read-out is a fixed linear functional of the vertices and skinning is
+ * linear in [v_posed;1] per joint, so   joint_q[n] = sum_j A[n,j]_3x3 . z[n,q,j] + A[n,j]_t * s[q,j]
+ * with z[n,q,j] = sum_v w_q[v] W[v,j] v_posed[n,v] = a row of  Z = [pose feature | betas] . MZ + Z0
+ * (one small GEMM; MZ is posedirs / shapedirs contracted with w_q (x) W once per asset set).
+ *   Z  (N, ldz): [np picked vertices x 3 (their own v_posed) | nx regressed joints x 24 x 3]
+ *   Wp (np,24) skinning weights of the picked vertices;  Sj (nx,24) = sum_v w_q[v] W[v,j]
+ * out: JX (N, np+nx, 3): picked vertices then regressed joints (no translation). */
+int nemo_b200_readout_fwd(const float* A, const float* Z, int ldz, const float* Wp, int np,
+                          const float* Sj, int nx, float* JX, int N, void* stream);
+/* dJX (N,np+nx,3) -> dA (N,24,12) (overwritten, or added to when accumulate != 0) and dZ (N, ldz)
+ * overwritten (pad columns zeroed). */
+int nemo_b200_readout_bwd(const float* A, const float* Z, int ldz, const float* Wp, int np,
+                          const float* Sj, int nx, const float* dJX, float* dA, int accumulate,
+                          float* dZ, int N, void* stream);
 
 /* joints49 = cat(JP, JX)[joint_map] (+ transl), hmr/smpl.py:33-37 + smplx SMPL.forward.
  * JX rows: np picked vertices then nx regressed joints; regressed joints receive rowsum[r]*transl

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(64) k_chain_fwd(const float* __restrict__ R, c
 }
 __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, const float* __restrict__ J, int js,
                                                   const int* __restrict__ parents, const float* __restrict__ dA,
-                                                  const float* __restrict__ dJP, float* __restrict__ dR,
+                                                  const float* __restrict__ dAt, const float* __restrict__ dJP,
+                                                  float* __restrict__ dR,
                                                   float* __restrict__ dJ, int N) {
   __shared__ int sp[NJ];
   if (threadIdx.x < NJ) sp[threadIdx.x] = parents[threadIdx.x];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(64) k_chain_bwd(const float* __restrict__ R, c
     const float* Rn = R + (size_t)n * 216;
     const float* Jn = J + (size_t)n * js;
     chain_fwd_frame(Rn, Jn, sp, G, Atmp, JPtmp);
-    chain_bwd_frame(Rn, Jn, sp, G, dA ? dA + (size_t)n * 288 : nullptr, dJP ? dJP + (size_t)n * 72 : nullptr, dG,
+    chain_bwd_frame(Rn, Jn, sp, G, dA ? dA + (size_t)n * 288 : nullptr, dAt ? dAt + (size_t)n * 288 : nullptr, dJP ? dJP + (size_t)n * 72 : nullptr, dG,
                     dR + (size_t)n * 216, dJl);
   } else {
     for (int k = 0; k < NJ * 3; ++k) dJl[k] = 0.f;
@@ -203,10 +204,11 @@ extern "C" int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride,
   NB_LAUNCH_CHECK("chain_fwd");
 }
 extern "C" int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents, const float* dA,
+                                   const float* dAt,
                                    const float* dJP, float* dR, float* dJ, int N, void* stream) {
   if (N == 0) return 0;
   NB_REQUIRE(R && J && parents && dR && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_bwd: bad args");
-  k_chain_bwd<<<cdiv(N, 64), 64, 0, S(stream)>>>(R, J, j_stride, parents, dA, dJP, dR, dJ, N);
+  k_chain_bwd<<<cdiv(N, 64), 64, 0, S(stream)>>>(R, J, j_stride, parents, dA, dAt, dJP, dR, dJ, N);
   NB_LAUNCH_CHECK("chain_bwd");
 }
 

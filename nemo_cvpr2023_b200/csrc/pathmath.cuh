@@ -44,18 +44,21 @@ NB_HD void chain_fwd_frame(const float* R, const float* J, const int* parents, f
 
 // Backward.  G must hold the forward world transforms.  dG (24,12) scratch.
 // dA (24,12) or NULL, dJP (24,3) or NULL -> dR (24,9), dJ (24,3) (both overwritten).
+// dA (24,12) and dAt (12,24: the same gradient transposed, as the skinning backward reduces it) are summed; either may
+// be NULL.
 NB_HD void chain_bwd_frame(const float* R, const float* J, const int* parents, const float* G,
-                           const float* dA, const float* dJP, float* dG, float* dR, float* dJ) {
+                           const float* dA, const float* dAt, const float* dJP, float* dG, float* dR, float* dJ) {
   for (int i = 0; i < NJ; ++i) {
     const float* Gi = G + 12 * i;
     float* dGi = dG + 12 * i;
     float at[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      float a3 = dA ? dA[12 * i + 4 * r + 3] : 0.f;
+      float a3 = (dA ? dA[12 * i + 4 * r + 3] : 0.f) + (dAt ? dAt[(4 * r + 3) * NJ + i] : 0.f);
       at[r] = a3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) dGi[4 * r + c] = (dA ? dA[12 * i + 4 * r + c] : 0.f) - a3 * J[3 * i + c];
+      for (int c = 0; c < 3; ++c)
+        dGi[4 * r + c] = (dA ? dA[12 * i + 4 * r + c] : 0.f) + (dAt ? dAt[(4 * r + c) * NJ + i] : 0.f) - a3 * J[3 * i + c];
       dGi[4 * r + 3] = a3 + (dJP ? dJP[3 * i + r] : 0.f);
     }
 #pragma unroll

@@ -220,6 +220,7 @@ class FitEngine:
         Np = N + 1
         z = lambda *s: torch.zeros(*s, device=d)
         nxr = self.ro['np'] + self.ro['nx']
+        ldz = self.ro['ldz']
         w = dict(
             raw=z(N), X=z(Np, self.ldx), warped=z(N), yn=z(self.V, 3),
             H1=z(Np, h), H2=z(Np, h), H3=z(Np, h), Y=z(Np, LDY),
@@ -227,11 +228,11 @@ class FitEngine:
             PO_m=z(N, 3 * VP), PO_o=z(N, 3 * VP), PO_r=z(N, 3 * VP), dPO=z(N, 3 * VP),
             A_m=z(N, 288), A_o=z(N, 288), A_r=z(N, 288), JP=z(N, 72), JPs=z(N, 72),
             R_o=z(N, 24, 9), R_r=z(N, 24, 9),
-            JX=z(N, max(nxr, 1), 3), j25=z(N, 25, 3), p2d=z(N, 25, 2), loss_all=z(N, 25, 2), view_acc=z(self.V, 2),
+            JX=z(N, max(nxr, 1), 3), Z=z(N, ldz), dZ=z(N, ldz), zb=z(ldz), dzb=z(ldz), j25=z(N, 25, 3), p2d=z(N, 25, 2), loss_all=z(N, 25, 2), view_acc=z(self.V, 2),
             E1=z(N, H_VP), head=z(N, 2 * L_VP), dhead=z(N, 2 * L_VP), D1=z(N, H_VP), D2=z(N, H_VP), D3=z(N, 126),
             Rdec=z(N * 21, 9), recon=z(N, 69), signs=torch.zeros(N, 3, 2, VP // 32, dtype=torch.int32, device=d),
             ll=z(N), acc=z(8), terms=z(8), wts=z(8), total=z(1),
-            d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
+            d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dAt=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
             dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, LDY), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.ldx),
             dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dbase=z(3 * VP),
             base=z(3, VP), J=z(72), vi=torch.zeros(N, dtype=torch.long, device=d),
@@ -246,6 +247,8 @@ class FitEngine:
         C = self.C_
         gemm(self.betas, C.Sp, w['base'], 1, 3 * VP, 10, 10, 3 * VP, 3 * VP, bias=C.vt.view(-1))
         gemm(self.betas, C.JSt, w['J'], 1, 72, 10, 10, 72, 72, bias=C.Jt)
+        ro = self.ro
+        gemm(self.betas, ro['MZ'][207:], w['zb'], 1, ro['ldz'], 10, 10, ro['ldz'], ro['ldz'], bias=ro['Z0'])
 
     def _motion_forward(self, w, N, view_idx, raw_phase, use_noise):
         mv, gp, C = self.g_motion.views, self.g_phase.views, self.Cc
@@ -272,10 +275,23 @@ class FitEngine:
         torch.sub(w['Y'][:N, 144:147], w['Y'][N:Np, 144:147], out=w['trans'])
 
     def _lbs_forward(self, w, N, R, PO, A, JP):
+        """pose feature -> pose blend shapes (planar, lbs.py:221-235) and the kinematic chain (lbs.py:337-404)"""
         C = self.C_
         lib.pose_feature(R, w['F'], LDF, N)
         gemm(w['F'], C.PD, PO, N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
         lib.chain_fwd(R, w['J'], 0, C.parents, A, JP, N)
+
+    def _joints_forward(self, w, N):
+        """The main mesh of a step is consumed only through 25 joints: kinematic joints come
+        from the chain, picked vertices and the regressed head joint from the read-out operators (csrc/readout.cu),
+        which contract the pose feature with pre-reduced blend shapes -- identical arithmetic up to fp32 summation
+        order, without the 6890-vertex mesh, its 20736-wide pose-blend GEMM or the skinning kernel."""
+        C, ro = self.C_, self.ro
+        lib.pose_feature(w['R'], w['F'], LDF, N)
+        lib.chain_fwd(w['R'], w['J'], 0, C.parents, w['A_m'], w['JP'], N)
+        if ro['np'] + ro['nx']:
+            gemm(w['F'], ro['MZ'], w['Z'], N, ro['ldz'], 207, LDF, ro['ldz'], ro['ldz'], bias=w['zb'])
+            lib.readout_fwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['JX'], N)
 
     # ------------------------------------------------------------------ the step
     def forward_backward(self, view_idx, frame_idx, update=True, phases=None, mode='step', detach_pose=False):
@@ -305,9 +321,7 @@ class FitEngine:
         ls = self.loss_scale
         acc = w['acc']   # 0 l1_sum, 1 kl_sum, 2 loss_3d, 3 gmm_sum, 4 kp, 5 instance
         if need_2d:
-            self._lbs_forward(w, N, w['R'], w['PO_m'], w['A_m'], w['JP'])
-            lib.skin_fwd(w['A_m'], w['PO_m'], w['base'], C.Wt, ro['Jx'] if ro['nx'] else None, ro['nx'],
-                         ro['slot'] if ro['np'] else None, ro['np'], None, w['JX'], N)
+            self._joints_forward(w, N)
             lib.joints_gather_fwd(w['JP'], w['JX'], ro['np'] + ro['nx'], ro['np'], self.map25, 25, w['trans'], None,
                                   w['j25'], N)
             lib.kp_loss_fwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox, self.focal,
@@ -366,21 +380,21 @@ class FitEngine:
                                0, self.V)
                 lib.joints_gather_bwd(w['dj25'], ro['np'] + ro['nx'], ro['np'], self.map25, 25, None, w['dJP'],
                                       w['dJX'], w['dtr'], N)
+                nq = ro['np'] + ro['nx']
+                if nq:
+                    lib.readout_bwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['dJX'],
+                                    w['dA'], 0, w['dZ'], N)
+                lib.chain_bwd(w['R'], w['J'], 0, C.parents, w['dA'] if nq else None, None, w['dJP'], dR,
+                              w['dJ'].zero_(), N)
                 if detach_pose:
                     # V4 opt_cam (:4060-4149): body rotmats detached, gradient reaches the MLP through the global
                     # orientation and the translation only
-                    pass
-                lib.skin_bwd(w['A_m'], w['PO_m'], w['base'], C.Wt, C.W2, ro['Jx'] if ro['nx'] else None, ro['nx'],
-                             ro['slot'] if ro['np'] else None, ro['np'], None, w['dJX'], None, 0.0, w['dPO'],
-                             w['dA'], N)
-                lib.chain_bwd(w['R'], w['J'], 0, C.parents, w['dA'], w['dJP'], dR, w['dJ'].zero_(), N)
-                if not detach_pose:
-                    gemm(w['dPO'], C.PD, dR.view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
-                         accumulate=True)
-                else:
                     dR[:, 1:].zero_()
+                elif nq:
+                    gemm(w['dZ'], ro['MZ'], dR.view(-1)[9:], N, 207, ro['ldz'], ro['ldz'], ro['ldz'], 216, transB=True,
+                         accumulate=True)
                 if self.compute_betas_grad:
-                    self._betas_grad(w, N, first=True)
+                    self._betas_grad(w, N, first=True, mesh=False)
             else:
                 dR.zero_()
                 w['dtr'].zero_()
@@ -390,13 +404,13 @@ class FitEngine:
                      gate_slope=0.01)
                 gemm(w['dE1'], vp['W1e'], w['d_aa'], N, 72, H_VP, H_VP, 72, 72, accumulate=True)
             if full and w_vp:
-                lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, C.W2, None, 0, None, 0, None, None, w['signs'],
-                             ls * w_vp / (N * NV * 3.0), w['dPO'], w['dA'], N)
-                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, w['dA'], None, w['dR_o'], w['dJ'].zero_(), N)
+                lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, None, w['signs'], ls * w_vp / (N * NV * 3.0),
+                             w['dPO'], w['dAt'], N)
+                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, None, w['dAt'], None, w['dR_o'], w['dJ'].zero_(), N)
                 gemm(w['dPO'], C.PD, w['dR_o'].view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
                      accumulate=True)
                 if self.compute_betas_grad:
-                    self._betas_grad(w, N, first=not need_2d)
+                    self._betas_grad(w, N, first=not need_2d, mesh=True)
                 lib.rodrigues_bwd(w['aa'].view(-1)[3:], 72, w['dR_o'].view(-1)[9:], 216, w['d_aa'].view(-1)[3:], 72,
                                   23, 1, N * 23, 0)
                 dR[:, 0].add_(w['dR_o'][:, 0])
@@ -426,11 +440,17 @@ class FitEngine:
         lib.combine_losses(acc, cache[wkey], 8, w['total'])
         return w, norm
 
-    def _betas_grad(self, w, N, first):
-        """d learned_betas: the reference accumulates it on every backward although no optimiser owns it."""
-        C = self.C_
-        lib.colsum(w['dPO'], w['dbase'], N, 3 * VP, 3 * VP, 0)
-        gemm(w['dbase'], C.Sp, self.betas_grad, 1, 10, 3 * VP, 3 * VP, 3 * VP, 10, transB=True, accumulate=True)
+    def _betas_grad(self, w, N, first, mesh):
+        """d learned_betas: the reference accumulates it on every backward although no optimiser owns it.
+        mesh=True: through the vertices (column sum of dPO); mesh=False: through the joint read-outs (dZ)."""
+        C, ro = self.C_, self.ro
+        if mesh:
+            lib.colsum(w['dPO'], w['dbase'], N, 3 * VP, 3 * VP, 0)
+            gemm(w['dbase'], C.Sp, self.betas_grad, 1, 10, 3 * VP, 3 * VP, 3 * VP, 10, transB=True, accumulate=True)
+        elif ro['np'] + ro['nx']:
+            lib.colsum(w['dZ'], w['dzb'], N, ro['ldz'], ro['ldz'], 0)
+            gemm(w['dzb'], ro['MZ'][207:], self.betas_grad, 1, 10, ro['ldz'], ro['ldz'], ro['ldz'], 10, transB=True,
+                 accumulate=True)
         gemm(w['dJ'], C.JSt, self.betas_grad, 1, 10, 72, 72, 72, 10, transB=True, accumulate=True)
 
     def _motion_backward(self, w, N, vi):
@@ -493,11 +513,13 @@ class FitEngine:
         use_noise = self.version >= 3 and self.training and self.args.code_noise > 0 and self.Cc > 0
         self._motion_forward(w, N, w['vi'], w['raw'], use_noise)
         self._shape(w)
-        self._lbs_forward(w, N, w['R'], w['PO_m'], w['A_m'], w['JP'])
+        self._joints_forward(w, N)
         ro = self.ro
-        V = torch.empty(N, NV, 3, device=self.dev) if want_vertices else None
-        lib.skin_fwd(w['A_m'], w['PO_m'], w['base'], C.Wt, ro['Jx'] if ro['nx'] else None, ro['nx'],
-                     ro['slot'] if ro['np'] else None, ro['np'], V, w['JX'], N)
+        V = None
+        if want_vertices:
+            V = torch.empty(N, NV, 3, device=self.dev)
+            gemm(w['F'], C.PD, w['PO_m'], N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
+            lib.skin_fwd(w['A_m'], w['PO_m'], w['base'], C.Wt, V, N)
         j = torch.empty(N, 25, 3, device=self.dev)
         lib.joints_gather_fwd(w['JP'], w['JX'], ro['np'] + ro['nx'], ro['np'], self.map25, 25,
                               w['trans'] if add_trans else None, None, j, N)

@@ -281,9 +281,8 @@ class SMPLConstants:
       PD      (207,3VP)   posedirs with columns permuted interleaved(v,c) -> planar(c,v)
       basis   (217,3VP)   [PD; Sp] for per-frame betas
       Jt      (72,)       J_regressor . v_template        JSt (10,72)  J_regressor . shapedirs (transposed)
-      Wt      (24,VP)     lbs_weights^T                   W2  (VP,8,4) the same, 3 joints per float4
-      Jx      (9,VP)      J_regressor_extra               rowsum (9,)
-      slot    int8 (VP,)  index into the 21 VertexJointSelector picks or -1
+      Wt      (24,VP)     lbs_weights^T
+      readout             joint read-out operators (make_readout)
     """
 
     def __init__(self, sm: dict, device='cuda'):
@@ -312,10 +311,11 @@ class SMPLConstants:
         wt = torch.zeros(24, VP)
         wt[:, :NV] = w.t()
         self.Wt = wt.to(dev).contiguous()
-        w2 = torch.zeros(VP, 8, 4)
-        w2[:NV, :, :3] = w.view(NV, 8, 3)
-        self.W2 = w2.to(dev).contiguous()
+        # host float64 copies for the read-out operators: basis (217, 3, NV), template (3, NV), weights (NV, 24)
+        self._host = dict(basis=torch.cat([pd.view(207, NV, 3), sd.permute(2, 0, 1)], 0).permute(0, 2, 1).double().contiguous(),
+                          vt=vt.t().double().contiguous(), w=w.double())
         self.set_readouts(np.asarray(sm['vertex_joint_ids']), jx)
+        self.no_readout = self.make_readout([], torch.zeros(0, NV))
         self.parents = torch.as_tensor(np.asarray(sm['parents']), dtype=torch.int32).to(dev)
         self.joint_map = torch.as_tensor(np.asarray(sm['joint_map']), dtype=torch.int32).to(dev)
         self.faces = np.asarray(sm['faces'])
@@ -325,18 +325,39 @@ class SMPLConstants:
                                                    'lbs_weights', 'J_regressor_extra')}
 
     def make_readout(self, pick_ids, jx_rows):
-        """(slot int8 (VP,), np, Jx (nx,VP), nx, rowsum (nx,)) for a set of vertex picks / regressor rows."""
+        """Read-out operators for a set of vertex picks (smplx VertexJointSelector) and regressor rows
+        (hmr/smpl.py:33-36), see csrc/readout.cu.  A read-out is linear in the mesh, so it is pre-contracted with
+        the pose / shape blend bases and the skinning weights once (float64 on the host):
+
+          MZ (207+nb, ldz), Z0 (ldz,): Z = [pose feature | betas] . MZ + Z0, columns [np x 3 | nx x 24 x 3]
+          Wp (np,24) weights of the picked vertices, Sj (nx,24) = sum_v Jx[r,v] W[v,j], rowsum (nx,)
+        """
         pick_ids = np.asarray(pick_ids, dtype=np.int64).reshape(-1)
         if len(set(pick_ids.tolist())) != len(pick_ids):
             raise ValueError('vertex pick ids must be unique')
-        slot = -np.ones(VP, np.int8)
-        slot[pick_ids] = np.arange(len(pick_ids), dtype=np.int8)
-        jx_rows = torch.as_tensor(jx_rows, dtype=torch.float32).reshape(-1, NV)
-        jxp = torch.zeros(jx_rows.shape[0], VP)
-        jxp[:, :NV] = jx_rows.cpu()
+        jx_rows = torch.as_tensor(jx_rows, dtype=torch.float32).reshape(-1, NV).cpu()
+        n_p, n_x = len(pick_ids), jx_rows.shape[0]
+        H = self._host
+        basis, vt, w = H['basis'], H['vt'], H['w']          # (K,3,NV), (3,NV), (NV,24)
+        K = basis.shape[0]
+        ldz = max(4, (3 * n_p + 72 * n_x + 3) // 4 * 4)
+        MZ = torch.zeros(K, ldz, dtype=torch.float64)
+        Z0 = torch.zeros(ldz, dtype=torch.float64)
+        ids = torch.as_tensor(pick_ids)
+        if n_p:
+            MZ[:, :3 * n_p] = basis[:, :, ids].permute(0, 2, 1).reshape(K, 3 * n_p)
+            Z0[:3 * n_p] = vt[:, ids].t().reshape(-1)
+        Sj = torch.zeros(n_x, 24, dtype=torch.float64)
+        for r in range(n_x):
+            B = jx_rows[r].double()[:, None] * w                                  # (NV,24)
+            o = 3 * n_p + 72 * r
+            MZ[:, o:o + 72] = (basis.reshape(K * 3, NV) @ B).reshape(K, 3, 24).permute(0, 2, 1).reshape(K, 72)
+            Z0[o:o + 72] = (vt @ B).t().reshape(-1)
+            Sj[r] = B.sum(0)
         dev = self.vt.device
-        return dict(slot=torch.from_numpy(slot).to(dev), np=len(pick_ids), Jx=jxp.to(dev).contiguous(),
-                    nx=jx_rows.shape[0], rowsum=jx_rows.double().sum(1).float().to(dev))
+        f32 = lambda t: t.float().to(dev).contiguous()
+        return dict(np=n_p, nx=n_x, ldz=ldz, MZ=f32(MZ), Z0=f32(Z0), Wp=f32(w[ids]) if n_p else None,
+                    Sj=f32(Sj) if n_x else None, rowsum=jx_rows.double().sum(1).float().to(dev))
 
     def set_readouts(self, pick_ids, jx_rows):
         self.readout = self.make_readout(pick_ids, jx_rows)
@@ -347,7 +368,9 @@ class _LBS(torch.autograd.Function):
     smplx VertexJointSelector / hmr.smpl.SMPL (hmr/smpl.py:33-36).
 
     rot (N,24,3,3); betas (1,nb) shared or (N,nb) per frame.
-    returns vertices (N,6890,3) [or None], posed joints JP (N,24,3), read-outs JX (N,np+nx,3)."""
+    returns vertices (N,6890,3) [or an empty tensor], posed joints JP (N,24,3), read-outs JX (N,np+nx,3).
+    The read-outs never touch the mesh (csrc/readout.cu); when no gradient arrives through the vertices the
+    backward skips the skinning kernel and the 20736-wide pose-blend dgrad altogether."""
 
     @staticmethod
     def forward(ctx, rot, betas, C, readout, want_vertices):
@@ -357,73 +380,97 @@ class _LBS(torch.autograd.Function):
         per_frame = betas.shape[0] != 1
         nb = betas.shape[1]
         dev = rot.device
+        ro = readout
+        nq = ro['np'] + ro['nx']
+        K = 207 + nb if per_frame else 207
+        ldf = (K + 3) // 4 * 4                # 16-byte rows: the GEMM reads F through TMA
+        F = torch.zeros((N, ldf), device=dev)
+        zb = None
         if per_frame:
             if betas.shape[0] != N:
                 raise ValueError('betas batch %d does not match pose batch %d' % (betas.shape[0], N))
-            K = 207 + nb
-            F = _new((N, K), rot)
-            F[:, 207:] = betas
+            F[:, 207:K] = betas
             basis, base = C.basis, C.vt
             J = _new((N, 72), rot)
             gemm(betas, C.JSt, J, N, 72, nb, nb, 72, 72, bias=C.Jt)
             js = 72
+            zb = ro['Z0']
         else:
-            K = 207
-            F = _new((N, K), rot)
             basis = C.PD
             base = _new((3, VP), rot)
             gemm(betas, C.Sp, base, 1, 3 * VP, nb, nb, 3 * VP, 3 * VP, bias=C.vt.view(-1))
             J = _new((72,), rot)
             gemm(betas, C.JSt, J, 1, 72, nb, nb, 72, 72, bias=C.Jt)
             js = 0
-        lib.pose_feature(rot, F, K, N)
-        PO = _new((N, 3 * VP), rot)
-        gemm(F, basis, PO, N, 3 * VP, K, K, 3 * VP, 3 * VP)
+            if nq:
+                zb = _new((ro['ldz'],), rot)
+                gemm(betas, ro['MZ'][207:], zb, 1, ro['ldz'], nb, nb, ro['ldz'], ro['ldz'], bias=ro['Z0'])
+        lib.pose_feature(rot, F, ldf, N)
         A = _new((N, 24, 12), rot)
         JP = _new((N, 24, 3), rot)
         lib.chain_fwd(rot, J, js, C.parents, A, JP, N)
-        ro = readout
-        V = _new((N, NV, 3), rot) if want_vertices else None
-        JX = _new((N, ro['np'] + ro['nx'], 3), rot)
-        lib.skin_fwd(A, PO, base, C.Wt, ro['Jx'] if ro['nx'] else None, ro['nx'],
-                     ro['slot'] if ro['np'] else None, ro['np'], V, JX if JX.numel() else None, N)
-        ctx.save_for_backward(rot, betas, F, PO, base, J, A)
-        ctx.C, ctx.ro, ctx.per_frame, ctx.js = C, ro, per_frame, js
-        if V is None:
-            V = torch.empty(0, device=dev)
+        PO = None
+        V = torch.empty(0, device=dev)
+        if want_vertices:
+            PO = _new((N, 3 * VP), rot)
+            gemm(F, basis, PO, N, 3 * VP, K, ldf, 3 * VP, 3 * VP)
+            V = _new((N, NV, 3), rot)
+            lib.skin_fwd(A, PO, base, C.Wt, V, N)
+        JX = _new((N, nq, 3), rot)
+        Z = None
+        if nq:
+            Z = _new((N, ro['ldz']), rot)
+            gemm(F, ro['MZ'], Z, N, ro['ldz'], K, ldf, ro['ldz'], ro['ldz'], bias=zb)
+            lib.readout_fwd(A, Z, ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], JX, N)
+        ctx.save_for_backward(rot, betas, PO, base, J, A, Z)
+        ctx.C, ctx.ro, ctx.per_frame, ctx.js, ctx.K = C, ro, per_frame, js, K
         return V, JP, JX
 
     @staticmethod
     def backward(ctx, dV, dJP, dJX):
-        rot, betas, F, PO, base, J, A = ctx.saved_tensors
-        C, ro = ctx.C, ctx.ro
-        N, K, nb = rot.shape[0], F.shape[1], betas.shape[1]
-        dV = None if dV is None or dV.numel() == 0 else _f32c(dV)
-        dJX = None if dJX is None or dJX.numel() == 0 else _f32c(dJX)
+        rot, betas, PO, base, J, A, Z = ctx.saved_tensors
+        C, ro, K = ctx.C, ctx.ro, ctx.K
+        N, nb = rot.shape[0], betas.shape[1]
+        ldz = ro['ldz']
+        dV = None if dV is None or dV.numel() == 0 or PO is None else _f32c(dV)
+        dJX = None if dJX is None or dJX.numel() == 0 or Z is None else _f32c(dJX)
         dJP = None if dJP is None else _f32c(dJP)
-        dPO = _new((N, 3 * VP), rot)
-        dA = _new((N, 24, 12), rot)
-        lib.skin_bwd(A, PO, base, C.Wt, C.W2, ro['Jx'] if ro['nx'] else None, ro['nx'],
-                     ro['slot'] if ro['np'] else None, ro['np'], dV, dJX, None, 0.0, dPO, dA, N)
+        dA = dZ = dPO = dAt = None
+        if dJX is not None:
+            dA, dZ = _new((N, 24, 12), rot), _new((N, ldz), rot)
+            lib.readout_bwd(A, Z, ldz, ro['Wp'], ro['np'], ro['Sj'], ro['nx'], dJX, dA, 0, dZ, N)
+        if dV is not None:
+            dPO, dAt = _new((N, 3 * VP), rot), _new((N, 12, 24), rot)
+            lib.skin_bwd(A, PO, base, C.Wt, dV, None, 0.0, dPO, dAt, N)
         dR = _new((N, 24, 9), rot)
         dJ = _new((N, 72), rot) if ctx.per_frame else torch.zeros(72, device=rot.device)
-        lib.chain_bwd(rot, J, ctx.js, C.parents, dA, dJP, dR, dJ, N)
+        lib.chain_bwd(rot, J, ctx.js, C.parents, dA, dAt, dJP, dR, dJ, N)
+        # dR[:, 1:] += d(pose feature), written in place through the leading dimension (pose_feature backward)
+        if dPO is not None:
+            gemm(dPO, C.PD, dR.view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True, accumulate=True)
+        if dZ is not None:
+            gemm(dZ, ro['MZ'], dR.view(-1)[9:], N, 207, ldz, ldz, ldz, 216, transB=True, accumulate=True)
         dbetas = None
-        need_b = ctx.needs_input_grad[1]
-        # dR[:, 1:] += dPO . PD^T, written in place through the leading dimension (pose_feature backward)
-        gemm(dPO, C.PD, dR.view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True, accumulate=True)
-        if ctx.per_frame:
-            if need_b:
+        if ctx.needs_input_grad[1]:
+            MZs = ro['MZ'][207:]
+            if ctx.per_frame:
                 dbetas = _new((N, nb), rot)
-                gemm(dPO, C.Sp, dbetas, N, nb, 3 * VP, 3 * VP, 3 * VP, nb, transB=True)
-                gemm(dJ, C.JSt, dbetas, N, nb, 72, 72, 72, nb, transB=True, accumulate=True)
-        else:
-            if need_b:
-                dbase = _new((3 * VP,), rot)
-                lib.colsum(dPO, dbase, N, 3 * VP, 3 * VP, 0)
+                gemm(dJ, C.JSt, dbetas, N, nb, 72, 72, 72, nb, transB=True)
+                if dPO is not None:
+                    gemm(dPO, C.Sp, dbetas, N, nb, 3 * VP, 3 * VP, 3 * VP, nb, transB=True, accumulate=True)
+                if dZ is not None:
+                    gemm(dZ, MZs, dbetas, N, nb, ldz, ldz, ldz, nb, transB=True, accumulate=True)
+            else:
                 dbetas = _new((1, nb), rot)
-                gemm(dbase, C.Sp, dbetas, 1, nb, 3 * VP, 3 * VP, 3 * VP, nb, transB=True)
-                gemm(dJ, C.JSt, dbetas, 1, nb, 72, 72, 72, nb, transB=True, accumulate=True)
+                gemm(dJ, C.JSt, dbetas, 1, nb, 72, 72, 72, nb, transB=True)
+                if dPO is not None:
+                    dbase = _new((3 * VP,), rot)
+                    lib.colsum(dPO, dbase, N, 3 * VP, 3 * VP, 0)
+                    gemm(dbase, C.Sp, dbetas, 1, nb, 3 * VP, 3 * VP, 3 * VP, nb, transB=True, accumulate=True)
+                if dZ is not None:
+                    dzb = _new((ldz,), rot)
+                    lib.colsum(dZ, dzb, N, ldz, ldz, 0)
+                    gemm(dzb, MZs, dbetas, 1, nb, ldz, ldz, ldz, nb, transB=True, accumulate=True)
         return dR.view(N, 24, 3, 3), dbetas, None, None, None
 
 

@@ -31,7 +31,7 @@ class BodyModel(nn.Module):
         betas = z(self.num_betas) if betas is None else betas
         full_pose = torch.cat([root_orient, pose_body, pose_hand], dim=-1)
         rot = Fn.batch_rodrigues(full_pose.reshape(-1, 3), kind=1).view(B, 24, 3, 3)
-        V, JP, _ = Fn.lbs_rotmats(rot, betas, C, want_vertices=True)
+        V, JP, _ = Fn.lbs_rotmats(rot, betas, C, readout=C.no_readout, want_vertices=True)
         if trans is not None:
             V, JP = V + trans.unsqueeze(1), JP + trans.unsqueeze(1)
         res = dict(v=V, f=self.f, Jtr=JP, full_pose=full_pose)

@@ -76,5 +76,5 @@ def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_
         rot = Fn.batch_rodrigues(pose.reshape(-1, 3), kind=1).view(B, 24, 3, 3)
     else:
         rot = pose.reshape(B, 24, 3, 3)
-    V, JP, _ = Fn.lbs_rotmats(rot, betas, C, want_vertices=True)
+    V, JP, _ = Fn.lbs_rotmats(rot, betas, C, readout=C.no_readout, want_vertices=True)
     return V, JP

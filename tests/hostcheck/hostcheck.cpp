@@ -22,7 +22,7 @@ void hc_chain_bwd(const float* R, const float* J, int js, const int* parents, co
   float G[288], dG[288], At[288], JPt[72];
   for (int n = 0; n < N; ++n) {
     chain_fwd_frame(R + 216 * n, J + js * n, parents, G, At, JPt);
-    chain_bwd_frame(R + 216 * n, J + js * n, parents, G, dA ? dA + 288 * n : nullptr, dJP ? dJP + 72 * n : nullptr, dG, dR + 216 * n, dJ + 72 * n);
+    chain_bwd_frame(R + 216 * n, J + js * n, parents, G, dA ? dA + 288 * n : nullptr, nullptr, dJP ? dJP + 72 * n : nullptr, dG, dR + 216 * n, dJ + 72 * n);
   }
 }
 void hc_project(const float* R, const float* t, float f, float cx, float cy, float eps, const float* p, float* uv, int P) {

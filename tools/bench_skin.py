@@ -19,17 +19,25 @@ A2 = torch.randn(N, 24, 12, device=dev, generator=g)
 PO = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
 PO2 = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
 dV = torch.randn(N, Fn.NV, 3, device=dev, generator=g)
-ro = C.readout
-nxr = ro['np'] + ro['nx']
-dJX = torch.randn(N, nxr, 3, device=dev, generator=g)
 V = torch.empty(N, Fn.NV, 3, device=dev)
-JX = torch.empty(N, nxr, 3, device=dev)
-dPO, dA = torch.empty_like(PO), torch.empty(N, 24, 12, device=dev)
+dPO, dAt = torch.empty_like(PO), torch.empty(N, 12, 24, device=dev)
 signs = torch.zeros(N, 3, 2, Fn.VP // 32, dtype=torch.int32, device=dev)
 l1 = torch.zeros(1, device=dev)
+ro = C.readout
+nq = ro['np'] + ro['nx']
+Fp = torch.randn(N, 208, device=dev, generator=g)
+Z = torch.empty(N, ro['ldz'], device=dev)
+dZ = torch.empty_like(Z)
+JX = torch.empty(N, nq, 3, device=dev)
+dJX = torch.randn(N, nq, 3, device=dev, generator=g)
+dA = torch.empty(N, 24, 12, device=dev)
 
 
 def timeit(fn, iters=10):
+    if os.environ.get('NCU_ONCE'):   # under ncu: one launch per case
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(3):
         fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,20 +50,20 @@ def timeit(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+def readout_fwd():
+    Fn.gemm(Fp, ro['MZ'], Z, N, ro['ldz'], 207, 208, ro['ldz'], ro['ldz'], bias=ro['Z0'])
+    lib.readout_fwd(A, Z, ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], JX, N)
+
+
 cases = [
-    ('fwd  V + all joints (np=%d nx=%d)' % (ro['np'], ro['nx']), 2,
-     lambda: lib.skin_fwd(A, PO, C.vt, C.Wt, ro['Jx'], ro['nx'], ro['slot'], ro['np'], V, JX, N)),
-    ('fwd  V only', 2, lambda: lib.skin_fwd(A, PO, C.vt, C.Wt, None, 0, None, 0, V, None, N)),
-    ('fwd  joints only (no V, nx=1)', 1,
-     lambda: lib.skin_fwd(A, PO, C.vt, C.Wt, ro['Jx'], 1, ro['slot'], ro['np'], None, JX, N)),
+    ('fwd  V', 2, lambda: lib.skin_fwd(A, PO, C.vt, C.Wt, V, N)),
     ('l1   two meshes + sign bits', 2, lambda: lib.skin_l1_fwd(A, PO, A2, PO2, C.vt, C.Wt, signs, l1, N)),
-    ('bwd  dV + dJX -> dPO, dA', 3,
-     lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, C.W2, ro['Jx'], ro['nx'], ro['slot'], ro['np'], dV, dJX, None, 0.0, dPO, dA, N)),
-    ('bwd  dJX only (nx=1) -> dPO, dA', 2,
-     lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, C.W2, ro['Jx'], 1, ro['slot'], ro['np'], None, dJX, None, 0.0, dPO, dA, N)),
-    ('bwd  signs -> dPO, dA', 2,
-     lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, C.W2, None, 0, None, 0, None, None, signs, 1e-3, dPO, dA, N)),
+    ('bwd  dV -> dPO, dAt', 3, lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAt, N)),
+    ('bwd  signs -> dPO, dAt', 2, lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, None, signs, 1e-3, dPO, dAt, N)),
+    ('read-outs fwd (np=%d nx=%d): Z GEMM + kernel' % (ro['np'], ro['nx']), 0, readout_fwd),
+    ('read-outs bwd: dA, dZ', 0,
+     lambda: lib.readout_bwd(A, Z, ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], dJX, dA, 0, dZ, N)),
 ]
 for name, streams, fn in cases:
     t = timeit(fn)
-    print('%-40s %.3f ms   %7.1f GB/s algorithmic (%d streams/frame)' % (name, t, streams * STREAM * N / t / 1e6, streams))
+    print('%-48s %.3f ms   %7.1f GB/s algorithmic (%d streams/frame)' % (name, t, streams * STREAM * N / t / 1e6, streams))
