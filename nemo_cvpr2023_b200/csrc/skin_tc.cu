@@ -60,16 +60,7 @@ struct AmatWriter {
       off[i][1] = kmajor_sw128(12 + c, j) - 12 * 128;
     }
   }
-  // src[s]: the 288 floats of slot s (already clamped to a valid frame)
-  template <typename SrcFn>
-  __device__ __forceinline__ void write(uint32_t am, int pt, SrcFn src) const {
-    float x[FB][3];
-#pragma unroll
-    for (int s = 0; s < FB; ++s) {
-      const float* p = src(s);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) x[s][i] = __ldg(p + pt + 96 * i);
-    }
+  __device__ __forceinline__ void store(uint32_t am, const float (&x)[FB][3]) const {
 #pragma unroll
     for (int s = 0; s < FB; ++s)
 #pragma unroll
@@ -80,6 +71,18 @@ struct AmatWriter {
         sts32(o, hi);
         sts32(o + AM_BYTES, lo);
       }
+  }
+  // src[s]: the 288 floats of slot s (already clamped to a valid frame)
+  template <typename SrcFn>
+  __device__ __forceinline__ void write(uint32_t am, int pt, SrcFn src) const {
+    float x[FB][3];
+#pragma unroll
+    for (int s = 0; s < FB; ++s) {
+      const float* p = src(s);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) x[s][i] = __ldg(p + pt + 96 * i);
+    }
+    store(am, x);
   }
 };
 
@@ -317,17 +320,18 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
 // accumulator (lanes = (f,r,c), columns = joints) into global dAt (N,12,24) with 16-byte vector reductions
 // (the 54 vertex tiles add up).
 struct BwdCfg {
-  static constexpr int WD_KB_BYTES = 64 * 128;       // one 32-vertex k block of [W hi | W lo]: 64 rows(j) x 128 bytes
+  static constexpr int WD_ROWS = 48;                 // [W hi (24 joints) | W lo (24 joints)]
+  static constexpr int WD_KB_BYTES = WD_ROWS * 128;  // one 32-vertex k block of [W hi | W lo]: 48 rows(j) x 128 bytes
   static constexpr int GT_KB_BYTES = NROW * 128;     // one k block of one tf32 part of G^T: 96 rows x 128 bytes
   static constexpr int GT_BYTES = 4 * GT_KB_BYTES;   // rows 96..127 read by an M = 128 MMA alias the next block (unused)
-  static constexpr int OFF_WD = 0;                               // 4 x 8 KB
+  static constexpr int OFF_WD = 0;                               // 4 x 6 KB
   static constexpr int OFF_AM = OFF_WD + 4 * WD_KB_BYTES;        // 2 buffers x [hi][lo] x 12 KB
   static constexpr int OFF_GT = OFF_AM + 4 * AM_BYTES;           // [hi][lo] x 48 KB
   static constexpr int OFF_TAIL = OFF_GT + 2 * GT_BYTES;         // 4 KB of zeros read by the last block's rows 96..127
   static constexpr int OFF_BARS = OFF_TAIL + 4096;
   static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
   static constexpr int TM_T = 0;        // T: 2 x 128 columns
-  static constexpr int TM_D = 256;      // dA^T: 2 x 64 columns
+  static constexpr int TM_D = 256;      // dA^T: 2 x 64 columns (48 used: [.W hi | .W lo])
   static constexpr int TM_W = 384;      // W tile: 32 hi + 32 lo columns
   static constexpr int TMEM_COLS = 512;
 };
@@ -339,20 +343,36 @@ struct SkinBwdArgs {
   float* dPO; float* dAt;
   float sign_scale;
   int N, groups_per_chunk, nchunks;
+  unsigned long long* dbg;  // TIMING instantiation only: per-role phase cycle counters
+  int ablate;  // debug (NEMO_B200_SKIN_ABLATE): 1 no dA reductions, 2 no G stores, 4 no dA MMAs, 8 no dPO stores, 16 no loads
 };
 
-template <bool HAS_DV, bool HAS_SIGNS>
-__global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
+// NWORK worker warps (8 or 16): warp = 4 * (frame slice of the group) + (TMEM lane quarter); 3 producer warps; 1 issuer
+template <bool HAS_DV, bool HAS_SIGNS, int NWORK, bool TIMING = false>
+__global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
+  uint32_t tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+  auto tick = [&](int i) {
+    if (TIMING) {
+      const uint32_t now = (uint32_t)clock();
+      tk[i] += now - tprev;
+      tprev = now;
+    }
+  };
+  auto tick_flush = [&](int role) {
+    if (TIMING && (threadIdx.x & 31) == 0)
+      for (int i = 0; i < 8; ++i) atomicAdd(a.dbg + role * 8 + i, (unsigned long long)tk[i]);
+  };
   using C_ = BwdCfg;
+  constexpr int THREADS = (NWORK + 4) * 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = sbase + C_::OFF_BARS;
   auto tfull = [&](int b) { return bars + 8u * b; };            // T[b] complete                     (commit)
-  auto tempty = [&](int b) { return bars + 8u * (2 + b); };     // workers done with T[b]            (256)
+  auto tempty = [&](int b) { return bars + 8u * (2 + b); };     // workers done with T[b]            (512)
   auto amfree = [&](int b) { return bars + 8u * (4 + b); };     // T GEMM done reading Amat[b]       (commit)
   auto d2full = [&](int b) { return bars + 8u * (6 + b); };     // dA^T[b] complete                  (commit)
   auto d2empty = [&](int b) { return bars + 8u * (8 + b); };    // dA^T[b] drained                   (96)
-  auto gfull = [&](int kb) { return bars + 8u * (10 + kb); };   // G^T k block written               (64)
+  auto gfull = [&](int kb) { return bars + 8u * (10 + kb); };   // G^T k block written               (128)
   auto gfree = [&](int kb) { return bars + 8u * (14 + kb); };   // dA GEMM done reading the k block  (commit)
   const uint32_t tmem_slot = bars + 8u * 18;
 
@@ -370,20 +390,21 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
-      mbar_init(tempty(b), 256);
+      mbar_init(tempty(b), NWORK * 32);
       mbar_init(amfree(b), 1);
       mbar_init(d2full(b), 1);
       mbar_init(d2empty(b), 96);
     }
     for (int kb = 0; kb < 4; ++kb) {
-      mbar_init(gfull(kb), 64);
+      mbar_init(gfull(kb), NWORK * 8);
       mbar_init(gfree(kb), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 7) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
+  constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3;  // warps [W_PROD, W_PROD+3): producers; W_ISSUE: dA GEMM
+  if (warp == W_ISSUE) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   // zero Amat (pad columns k = 24..31), G^T and its tail
-  for (int i = tid; i < (C_::OFF_BARS - C_::OFF_AM) / 16; i += 384)
+  for (int i = tid; i < (C_::OFF_BARS - C_::OFF_AM) / 16; i += THREADS)
     sts128(sbase + C_::OFF_AM + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   tc_fence_before();
   __syncthreads();
@@ -401,8 +422,10 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
       h[k] = __float_as_uint(hi);
       l[k] = __float_as_uint(lo);
       const uint32_t o = sbase + C_::OFF_WD + (uint32_t)(warp * C_::WD_KB_BYTES);
-      sts32(o + kmajor_sw128(k, lane), hi);
-      sts32(o + kmajor_sw128(32 + k, lane), lo);
+      if (k < NJ) {
+        sts32(o + kmajor_sw128(k, lane), hi);
+        sts32(o + kmajor_sw128(NJ + k, lane), lo);
+      }
     }
     const uint32_t tw = tmem_base + ((uint32_t)(warp * 32) << 16) + C_::TM_W;
     tmem_st32(tw, h);
@@ -414,15 +437,15 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
   __syncthreads();
   tc_fence_after();
   constexpr uint32_t idesc_t = umma_idesc_tf32(128, NROW, 0, 0);
-  constexpr uint32_t idesc_d64 = umma_idesc_tf32(128, 64, 0, 0);
+  constexpr uint32_t idesc_d48 = umma_idesc_tf32(128, C_::WD_ROWS, 0, 0);
   constexpr uint32_t idesc_d32 = umma_idesc_tf32(128, 32, 0, 0);
 
-  if (warp >= 4 && warp < 7) {
+  if (warp >= W_PROD && warp < W_ISSUE) {
     // ------------------------------------------------------------------ producers: Amat, T GEMM issue, dA^T drain
-    const int pt = tid - 128;
+    const int pt = tid - W_PROD * 32;
     AmatWriter aw;
     aw.init(pt);
-    const int row = (warp & 3) * 32 + lane;  // accumulator lane = (f, r, c)
+    const int row = (warp & 3) * 32 + lane;  // accumulator lane = (f, r, c); W_PROD % 4 == 0
     const int rf = row / 12, rq = row % 12;
     auto drain = [&](int gi) {
       const int b = gi & 1;
@@ -432,13 +455,13 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
       const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C_::TM_D + b * 64;
       tmem_ld16(ta, t);
       tmem_ld8(ta + 16, t + 16);
-      tmem_ld16(ta + 32, u);
-      tmem_ld8(ta + 48, u + 16);
+      tmem_ld16(ta + NJ, u);
+      tmem_ld8(ta + NJ + 16, u + 16);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(d2empty(b));
       const int n = group_of(gi) * FB + rf;
-      if (n <= last) {
+      if (n <= last && !(a.ablate & 1)) {
         float* d = a.dAt + (size_t)n * 288 + rq * 24;
 #pragma unroll
         for (int j = 0; j < NJ; j += 4)
@@ -448,13 +471,24 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
                      __uint_as_float(t[j + 3]) + __uint_as_float(u[j + 3]));
       }
     };
-    for (int gi = 0; gi < ng; ++gi) {
+    // The transforms of group gi + 2 are fetched into registers and the T GEMM of group gi + 1 is issued BEFORE this
+    // thread blocks in the drain of group gi: the workers never wait for T.
+    float x[FB][3];
+    auto fetch = [&](int gi) {
+      const int n0 = group_of(gi) * FB;
+#pragma unroll
+      for (int s = 0; s < FB; ++s) {
+        const float* p = a.A + (size_t)min(n0 + s, last) * 288 + pt;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[s][i] = __ldg(p + 96 * i);
+      }
+    };
+    auto issue_t = [&](int gi) {
       const int b = gi & 1;
       const uint32_t use = gi >> 1;
       if (use > 0) mbar_wait(amfree(b), (use - 1) & 1);
       const uint32_t am = sbase + C_::OFF_AM + b * 2 * AM_BYTES;
-      const int n0 = group_of(gi) * FB;
-      aw.write(am, pt, [&](int s) { return a.A + (size_t)min(n0 + s, last) * 288; });
+      aw.store(am, x);
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 96;" ::: "memory");
       if (pt == 0) {
@@ -473,43 +507,61 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
         umma_commit(tfull(b));
         umma_commit(amfree(b));
       }
-      if (gi > 0) drain(gi - 1);
+    };
+    fetch(0);
+    issue_t(0);
+    if (ng > 1) fetch(1);
+    tprev = (uint32_t)clock();
+    for (int gi = 0; gi < ng; ++gi) {
+      if (gi + 1 < ng) {
+        issue_t(gi + 1);
+        tick(0);
+        if (gi + 2 < ng) fetch(gi + 2);
+      }
+      drain(gi);
+      tick(1);
     }
-    drain(ng - 1);
-  } else if (warp == 7) {
+    tick_flush(1);
+  } else if (warp == W_ISSUE) {
     // ------------------------------------------------------------------ dA GEMM issuer
     if (lane == 0) {
       const uint64_t gh0 = umma_smem_desc(sbase + C_::OFF_GT, 16, 1024, LAYOUT_SW128);
       const uint64_t wd0 = umma_smem_desc(sbase + C_::OFF_WD, 16, 1024, LAYOUT_SW128);
+      tprev = (uint32_t)clock();
       for (int gi = 0; gi < ng; ++gi) {
         const int b = gi & 1;
         const uint32_t use = gi >> 1;
         const uint32_t d = tmem_base + C_::TM_D + b * 64;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
+          tick(4 + kb);
           mbar_wait(gfull(kb), gi & 1);
+          tick(kb);
           if (kb == 0 && use > 0) mbar_wait(d2empty(b), (use - 1) & 1);
           tc_fence_after();
+          if (!(a.ablate & 4))
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t go = kb * C_::GT_KB_BYTES + ks * 32, wo = kb * C_::WD_KB_BYTES + ks * 32;
             const uint64_t gh = umma_desc_advance(gh0, go), gl = umma_desc_advance(gh0, C_::GT_BYTES + go);
             const uint64_t wd = umma_desc_advance(wd0, wo);
-            umma_tf32(d, gh, wd, idesc_d64, (kb | ks) ? 1u : 0u);   // [G_hi.W_hi | G_hi.W_lo]
-            umma_tf32(d, gl, wd, idesc_d32, 1u);                    // += G_lo.W_hi
+            umma_tf32(d, gh, wd, idesc_d48, (kb | ks) ? 1u : 0u);   // [G_hi.W_hi | G_hi.W_lo]
+            // += G_lo.W_hi (N = 32: columns 24..31 also receive G_lo.W_lo of joints 0..7, a valid 4th-order term)
+            umma_tf32(d, gl, wd, idesc_d32, 1u);
           }
           umma_commit(gfree(kb));
         }
         umma_commit(d2full(b));
       }
+      tick_flush(2);
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ workers: two threads per vertex
-    // warps 0-3 take frames 0-3 of every group, warps 8-11 frames 4-7 (same TMEM lane quarter = warp & 3 = same
-    // warp scheduler and same G^T k block)
-    constexpr int FH = FB / 2;
-    const int wq = warp & 3, half = warp >> 3;
+    // ------------------------------------------------------------------ workers: four threads per vertex
+    // warp = 4 * (frame pair) + (TMEM lane quarter): the four warps of a quarter share one warp scheduler and one
+    // G^T k block and take two frames of the group each, so their barrier / TMEM / HBM latencies overlap
+    constexpr int FH = FB * 4 / NWORK;  // frames of the group per worker warp
+    const int wq = warp & 3, half = warp >> 2;
     const int v = v0 + wq * 32 + lane;
     const bool real = v < NV;
     float bs[3];
@@ -529,6 +581,7 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
     uint32_t sA = 0u, sB = 0u;  // this half's 24 sign words, one per lane
     auto load_in = [&](int gi, float (&p)[FH][3], float (&d)[FH][3], uint32_t& w) {
       const int n0 = group_of(gi < ng ? gi : ng - 1) * FB + half * FH;
+      if (a.ablate & 16) return;
       if (HAS_SIGNS) {
         const int fc = lane >> 1;  // word (f*3 + c)*2 + {pos, neg}
         const int n = min(n0 + fc / 3, last);
@@ -554,6 +607,13 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
                     float (&dn)[FH][3], uint32_t& swn) {
       const int b = gi & 1;
       const int n0 = group_of(gi) * FB + half * FH;
+      if (TIMING) {  // force the arrival of this group's inputs (prefetched during the previous group)
+        float acc = 0.f;
+        for (int f = 0; f < FH; ++f)
+          for (int c = 0; c < 3; ++c) acc += po[f][c] + (HAS_DV ? dv[f][c] : 0.f);
+        if (acc == 1.2345e-30f) tk[7] += 1;
+        tick(0);
+      }
       load_in(gi + 1, pn, dn, swn);
       // ---- upstream gradient of the vertex in each frame
       if (HAS_SIGNS) {
@@ -568,21 +628,29 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
           }
       }
       // ---- dPO = R^T dv from the T rows in TMEM (all of this half's rows in one batch of loads)
+      tick(1);
       mbar_wait(tfull(b), (gi >> 1) & 1);
+      tick(2);
       tc_fence_after();
       uint32_t t[FH * 12];
       const uint32_t ta = tmem_base + lane_addr + C_::TM_T + b * 128 + half * (FH * 12);
+      static_assert(FH == 2 || FH == 4, "TMEM loads below fetch 24 or 48 columns");
       tmem_ld16(ta, t);
-      tmem_ld16(ta + 16, t + 16);
-      tmem_ld16(ta + 32, t + 32);
+      if (FH == 2) {
+        tmem_ld8(ta + 16, t + 16);
+      } else {
+        tmem_ld16(ta + 16, t + 16);
+        tmem_ld16(ta + 32, t + 32);
+      }
       tmem_ld_wait();
+      tick(3);
       tc_fence_before();
       mbar_arrive(tempty(b));
       {
         float* d = a.dPO + (size_t)n0 * (3 * VP) + v;
 #pragma unroll
         for (int f = 0; f < FH; ++f) {
-          if (n0 + f <= last) {  // warp-uniform
+          if (n0 + f <= last && !(a.ablate & 8)) {  // warp-uniform
 #pragma unroll
             for (int c = 0; c < 3; ++c)
               __stcs(d + (size_t)f * (3 * VP) + c * VP,
@@ -592,7 +660,10 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
         }
       }
       // ---- G^T for the dA GEMM (the previous group's MMAs over this k block must have finished reading it)
+      tick(4);
       if (gi > 0) mbar_wait(gfree(wq), (gi - 1) & 1);
+      tick(5);
+      if (!(a.ablate & 2))
 #pragma unroll
       for (int f = 0; f < FH; ++f) {
         const float ph[3] = {bs[0] + po[f][0], bs[1] + po[f][1], bs[2] + po[f][2]};
@@ -609,16 +680,19 @@ __global__ void __launch_bounds__(384, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
       }
       fence_proxy_async_smem();
       mbar_arrive(gfull(wq));
+      tick(6);
     };
     load_in(0, pA, dA_, sA);
+    tprev = (uint32_t)clock();
     for (int gi = 0; gi < ng; gi += 2) {
       body(gi, pA, dA_, sA, pB, dB_, sB);
       if (gi + 1 < ng) body(gi + 1, pB, dB_, sB, pA, dA_, sA);
     }
+    tick_flush(0);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 7) {
+  if (warp == W_ISSUE) {
     tc_fence_after();
     tmem_dealloc<C_::TMEM_COLS>(tmem_base);
   }
@@ -655,16 +729,51 @@ int launch_fwd(const SkinArgs& a, cudaStream_t s) {
   NB_LAUNCH_CHECK("skin_tc_fwd");
 }
 
-template <bool HAS_DV, bool HAS_SIGNS>
-int launch_bwd(const SkinBwdArgs& a, cudaStream_t s) {
+template <bool HAS_DV, bool HAS_SIGNS, int NWORK>
+int launch_bwd_n(const SkinBwdArgs& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<HAS_DV, HAS_SIGNS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<HAS_DV, HAS_SIGNS, NWORK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BwdCfg::SMEM_BYTES));
     configured = true;
   }
-  k_skin_tc_bwd<HAS_DV, HAS_SIGNS><<<NT_V * a.nchunks, 384, BwdCfg::SMEM_BYTES, s>>>(a);
+  k_skin_tc_bwd<HAS_DV, HAS_SIGNS, NWORK><<<NT_V * a.nchunks, (NWORK + 4) * 32, BwdCfg::SMEM_BYTES, s>>>(a);
   NB_LAUNCH_CHECK("skin_tc_bwd");
+}
+
+// NEMO_B200_SKIN_TIMING=1 (debug): run the instrumented dV kernel, synchronise and print the phase counters
+int launch_bwd_timing(SkinBwdArgs a, cudaStream_t s) {
+  static unsigned long long* dbg = nullptr;
+  if (!dbg) NB_CUDA(cudaMalloc(&dbg, 24 * sizeof(unsigned long long)));
+  NB_CUDA(cudaMemsetAsync(dbg, 0, 24 * sizeof(unsigned long long), s));
+  a.dbg = dbg;
+  NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<true, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               BwdCfg::SMEM_BYTES));
+  k_skin_tc_bwd<true, false, 8, true><<<NT_V * a.nchunks, 12 * 32, BwdCfg::SMEM_BYTES, s>>>(a);
+  NB_CUDA(cudaStreamSynchronize(s));
+  unsigned long long h[24];
+  NB_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+  const double groups = (double)NT_V * cdiv(a.N, FB);
+  static const char* names[3][8] = {
+      {"inputs arrive", "issue prefetch+signs", "wait tfull", "tmem ld", "dPO", "wait gfree", "G phase", "-"},
+      {"issue_t", "fetch+drain", "-", "-", "-", "-", "-", "-"},
+      {"wait gfull0", "wait gfull1", "wait gfull2", "wait gfull3", "mma0", "mma1", "mma2", "mma3"}};
+  const double per[3] = {8.0, 3.0, 1.0};  // warps per role
+  for (int r = 0; r < 3; ++r) {
+    fprintf(stderr, "[skin_bwd timing] role %d:", r);
+    for (int i = 0; i < 8; ++i)
+      if (names[r][i][0] != '-') fprintf(stderr, "  %s %.0f", names[r][i], (double)h[r * 8 + i] / groups / per[r]);
+    fprintf(stderr, "  (cycles per group per warp)\n");
+  }
+  return 0;
+}
+
+template <bool HAS_DV, bool HAS_SIGNS>
+int launch_bwd(const SkinBwdArgs& a, cudaStream_t s) {
+  static const int timing = [] { const char* e = getenv("NEMO_B200_SKIN_TIMING"); return e ? atoi(e) : 0; }();
+  if (timing && HAS_DV && !HAS_SIGNS) return launch_bwd_timing(a, s);
+  static const int nwork = [] { const char* e = getenv("NEMO_B200_SKIN_BWD_WARPS"); return e ? atoi(e) : 16; }();
+  return nwork == 8 ? launch_bwd_n<HAS_DV, HAS_SIGNS, 8>(a, s) : launch_bwd_n<HAS_DV, HAS_SIGNS, 16>(a, s);
 }
 
 }  // namespace
@@ -701,6 +810,8 @@ extern "C" int nemo_b200_skin_bwd(const float* A, const float* PO, const float* 
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.dV = dV; a.signs = signs;
   a.sign_scale = sign_scale; a.dPO = dPO; a.dAt = dAt; a.N = N;
   chunking(N, FB, a.groups_per_chunk, a.nchunks);
+  static const int abl = [] { const char* e = getenv("NEMO_B200_SKIN_ABLATE"); return e ? atoi(e) : 0; }();
+  a.ablate = abl;
   NB_CUDA(cudaMemsetAsync(dAt, 0, sizeof(float) * (size_t)N * 288, s));  // vertex tiles accumulate with reductions
   if (dV && signs) return launch_bwd<true, true>(a, s);
   if (dV) return launch_bwd<true, false>(a, s);
