@@ -172,13 +172,13 @@ def k7_roofline(dev, iters=10):
     PO = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
     dV = torch.randn(N, Fn.NV, 3, device=dev, generator=g)
     Vout = torch.empty(N, Fn.NV, 3, device=dev)
-    dPO, dAt = torch.empty_like(PO), torch.empty(N, 12, 24, device=dev)
+    dPO, dAs = torch.empty_like(PO), torch.empty(N, 24, 12, device=dev)
 
     def fwd():
         lib.skin_fwd(A, PO, C.vt, C.Wt, Vout, N)
 
     def bwd():
-        lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAt, N)
+        lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAs, N)
 
     out = {}
     for name, fn in (('fwd', fwd), ('bwd', bwd)):

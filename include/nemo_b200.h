@@ -95,7 +95,7 @@ int nemo_b200_pose_feature(const float* R, float* F, int ldf, int N, void* strea
  * out: A (N,24,12) relative 3x4 transforms, JP (N,24,3) posed joints. */
 int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride, const int* parents,
                         float* A, float* JP, int N, void* stream);
-/* dA (N,24,12) and dAt (N,12,24) (the same gradient transposed, as nemo_b200_skin_bwd reduces it) are summed;
+/* dA (N,24,12) and dAt (N,12,24) (the same gradient transposed per frame) are summed;
  * either may be NULL.  dR (N,24,9) overwritten; dJ (N,24,3) overwritten when j_stride != 0, else (24,3)
  * ACCUMULATED with atomics (caller zeroes). */
 int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents,
@@ -112,11 +112,11 @@ int nemo_b200_skin_fwd(const float* A, const float* PO, const float* base, const
                        float* V, int N, void* stream);
 /* backward.  Upstream gradient of the vertices = dV (N,6890,3) [may be NULL]
  *   + sign_scale * sign bits [signs may be NULL]; at least one of the two.
- * out: dPO (N,3,VP) overwritten, dAt (N,12,24) overwritten (TRANSPOSED per frame: dAt[n][r*4+c][j];
+ * out: dPO (N,3,VP) overwritten, dA (N,24,12) overwritten (dA[n][j][r*4+c], the layout of A;
  * nemo_b200_chain_bwd consumes it as is).  d base = column sum of dPO. */
 int nemo_b200_skin_bwd(const float* A, const float* PO, const float* base, const float* Wt,
                        const float* dV, const uint32_t* signs, float sign_scale,
-                       float* dPO, float* dAt, int N, void* stream);
+                       float* dPO, float* dA, int N, void* stream);
 /* fused vertex-to-vertex L1 of MultiViewModel.vposer_loss (nemo/neural_motion_model.py:2792-2797):
  * l1_sum[0] += sum_{n,v,c} | v_b - v_a |  (mesh a = "orig", carries the gradient; mesh b = detached
  * reconstruction).  signs (N,3,2,VP/32) uint32 receives the (v_a > v_b, v_a < v_b) bit masks that

@@ -12,6 +12,9 @@
 // reads, prefetched one group ahead) and writes the vertex (forward) or dPO = R^T dv and its 12 G values (backward).
 // No per-vertex intermediate reaches HBM.  Joint read-outs are NOT done here: they are linear functionals of the
 // mesh and are evaluated without the mesh (readout.cu).
+#ifndef NB_MBAR_SLEEP
+#define NB_MBAR_SLEEP 32
+#endif
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -41,11 +44,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "r"(taddr)
                : "memory");
 }
-// 16-byte vector reduction (sm_90+): one L2 atomic transaction for four consecutive floats
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // The 96 producer threads turn the 3x4 transforms of a group of 8 frame slots (8 x 24 x 12 floats) into the K-major
 // B operand of the T GEMM (row = slot*12 + (r,c), k = joint), tf32 hi / lo.  Thread pt owns elements pt, pt+96,
 // pt+192 of every slot's 288, so its shared-memory offsets are loop invariant (two variants: the swizzle phase of
@@ -304,52 +302,69 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
 }
 
 // ================================================================================================ backward
-// Per vertex tile and group of 8 frames, two GEMMs on tcgen05:
-//   T[v, (f,12)]    = W[v, :] . Amat[:, (f,12)]      A operand (W tile, tf32 hi / lo) lives in TENSOR MEMORY, so only the
-//                                                    3 KB B operand is fetched from shared memory per MMA
-//   dA^T[(f,12), j] = sum_v G^T[(f,12), v] . W[v, j] G[v,(f,r,c)] = dv[f,v,r] * [v_posed;1][c]
-// The worker thread of vertex v reads the rotation rows of T from its TMEM lane, assembles dv (upstream dV and / or
-// the L1 sign bits), writes dPO = R^T dv (coalesced planar) and scatters G (raw fp32 = the hi operand, the tensor core
-// ignores the low 13 mantissa bits) and lo = G - trunc(G) into the K-major A operand of the second GEMM (row =
-// (f,r,c), k = vertex: a warp writes one full 128-byte swizzled row per store, conflict free).
-// The B operand of the second GEMM is [W hi | W lo] side by side (64 rows), so 3xTF32 costs two MMAs per k step
-// instead of three and G^T is fetched twice instead of three times:
-//   D[:, 0:32] += G_hi.W_hi + G_lo.W_hi      D[:, 32:64] += G_hi.W_lo        dA^T = D[:, j] + D[:, 32+j]
-// G^T is synchronised per 32-vertex k block (the two worker warps of a TMEM lane quarter share one warp scheduler
-// and one k block), so the MMAs of one block overlap the G writes of the others.  Three producer warps drain the
-// accumulator (lanes = (f,r,c), columns = joints) into global dAt (N,12,24) with 16-byte vector reductions
-// (the 54 vertex tiles add up).
+// Per vertex tile and group of 8 frames, two GEMMs on tcgen05, BOTH with their constant operand in TENSOR MEMORY (so
+// the only shared-memory operand traffic is the per-frame data):
+//   T[v, (f,12)]    = W[v, :] . Amat[:, (f,12)]        A operand = W tile (lane = vertex, tf32 hi / lo columns)
+//   dA[j, (f,12)]   = sum_v W^T[j, v] . G[v, (f,12)]   A operand = [W_hi^T ; W_lo^T] stacked in the lanes (hi: lanes
+//                                                      0..23, lo: lanes 32..55), K = the 128 vertices of the tile
+// G[v,(f,r,c)] = dv[f,v,r] * [v_posed;1][c]: the worker thread of a vertex scatters its 12 values per frame into the
+// K-major B operand (row = (f,r,c), k = vertex: a warp writes one full swizzled 128-byte row per store, conflict
+// free), raw fp32 as the hi part (the tensor core ignores the low 13 mantissa bits) and G - trunc(G) as the lo part.
+// (An MN-major G -- 16-byte stores per thread -- was measured: tf32 MN-major operands are fetched at ~32 bytes per
+// clock, which made the dA GEMM the bottleneck.)  Stacking W hi / lo in the accumulator lanes makes 3xTF32 two MMAs
+// per k step and G is fetched from shared memory exactly once per part:
+//   D[0:24]  += W_hi^T.G_hi + W_hi^T.G_lo        D[32:56] += W_lo^T.G_hi (+ W_lo^T.G_lo)       dA = D[j] + D[32+j]
+// G is synchronised per 32-vertex k block (the four worker warps of a TMEM lane quarter share one k block), so the
+// MMAs of one block overlap the G writes of the others.
+// Roles (23 warps): 16 workers; 3 Amat producers (+ T GEMM issue); 1 dA GEMM issuer; 2 drain warps (TMEM lane
+// quarters 0 / 1: the W_lo half goes through a shared staging tile, the W_hi warp adds it and reduces into global
+// dA (N,24,12) with 16-byte vector reductions -- the 54 vertex tiles add up); 1 loader feeding the input ring.
 struct BwdCfg {
-  static constexpr int WD_ROWS = 48;                 // [W hi (24 joints) | W lo (24 joints)]
-  static constexpr int WD_KB_BYTES = WD_ROWS * 128;  // one 32-vertex k block of [W hi | W lo]: 48 rows(j) x 128 bytes
-  static constexpr int GT_KB_BYTES = NROW * 128;     // one k block of one tf32 part of G^T: 96 rows x 128 bytes
-  static constexpr int GT_BYTES = 4 * GT_KB_BYTES;   // rows 96..127 read by an M = 128 MMA alias the next block (unused)
-  static constexpr int OFF_WD = 0;                               // 4 x 6 KB
-  static constexpr int OFF_AM = OFF_WD + 4 * WD_KB_BYTES;        // 2 buffers x [hi][lo] x 12 KB
-  static constexpr int OFF_GT = OFF_AM + 4 * AM_BYTES;           // [hi][lo] x 48 KB
-  static constexpr int OFF_TAIL = OFF_GT + 2 * GT_BYTES;         // 4 KB of zeros read by the last block's rows 96..127
-  static constexpr int OFF_BARS = OFF_TAIL + 4096;
+  static constexpr int GT_LO = NROW * 128;               // rows 96..191 of a k block: the lo part
+  static constexpr int GT_KB_BYTES = 2 * NROW * 128;     // one 32-vertex k block of G: [hi | lo] = 192 rows x 128 B
+  static constexpr int OFF_AM = 0;                       // [hi][lo] x 12 KB
+  static constexpr int OFF_G = OFF_AM + 2 * AM_BYTES;    // 4 k blocks x 24 KB
+  // input ring: the pose offsets (planar: 3 x 512 bytes per frame) and the upstream vertex gradient (interleaved xyz:
+  // 1536 bytes per frame) of NSTAGE frame groups are in flight as 32 bulk async copies per group, one per lane of the
+  // loader warp -- the HBM latency is covered by the ring, not by registers.  The frame stride of dV (82 680 bytes) is
+  // only 8-byte aligned: an odd frame is copied from 8 bytes earlier (+16 bytes) and read at an 8-byte offset.
+  static constexpr int NSTAGE = 3;
+  static constexpr int ST_PO_BYTES = FB * 3 * TILE_V * 4;
+  static constexpr int DV_SLOT = TILE_V * 12 + 16;
+  static constexpr int ST_DV_BYTES = FB * DV_SLOT;
+  static constexpr int ST_BYTES = ST_PO_BYTES + ST_DV_BYTES;
+  static constexpr int OFF_ST = OFF_G + 4 * GT_KB_BYTES;
+  // accumulator staging: three partial sums (. G_hi and . G_lo of the W_hi lanes, . G_hi of the W_lo lanes), each laid
+  // out exactly like the group's slab of global dA: [frame][joint][12] (a lane = joint writes 16-byte pieces with a
+  // 48-byte stride: conflict free)
+  static constexpr int STG_BYTES = FB * 288 * 4;
+  static constexpr int OFF_STG = OFF_ST + NSTAGE * ST_BYTES;
+  static constexpr int OFF_BARS = OFF_STG + 3 * STG_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
-  static constexpr int TM_T = 0;        // T: 2 x 128 columns
-  static constexpr int TM_D = 256;      // dA^T: 2 x 64 columns (48 used: [.W hi | .W lo])
-  static constexpr int TM_W = 384;      // W tile: 32 hi + 32 lo columns
+  static constexpr int TM_T = 0;        // T: 96 columns
+  static constexpr int TM_WT = 96;      // [W_hi^T ; W_lo^T]: 128 columns (k = vertex)
+  static constexpr int TM_D = 224;      // dA: 192 columns [. G_hi | . G_lo]
+  static constexpr int TM_W = 416;      // W tile: 32 hi + 32 lo columns
   static constexpr int TMEM_COLS = 512;
 };
 static_assert(BwdCfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(BwdCfg::OFF_G % 1024 == 0, "swizzled operand alignment");
 
 struct SkinBwdArgs {
   const float* A; const float* PO; const float* base; const float* Wt;
   const float* dV; const uint32_t* signs;
-  float* dPO; float* dAt;
+  float* dPO; float* dA;
   float sign_scale;
   int N, groups_per_chunk, nchunks;
   unsigned long long* dbg;  // TIMING instantiation only: per-role phase cycle counters
   int ablate;  // debug (NEMO_B200_SKIN_ABLATE): 1 no dA reductions, 2 no G stores, 4 no dA MMAs, 8 no dPO stores, 16 no loads
 };
 
-// NWORK worker warps (8 or 16): warp = 4 * (frame slice of the group) + (TMEM lane quarter); 3 producer warps; 1 issuer
-template <bool HAS_DV, bool HAS_SIGNS, int NWORK, bool TIMING = false>
-__global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
+constexpr int NWORK = 16;                 // worker warps: warp = 4 * (frame pair of the group) + (TMEM lane quarter)
+constexpr int BWD_THREADS = (NWORK + 9) * 32;
+
+template <bool HAS_DV, bool HAS_SIGNS, bool TIMING = false>
+__global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
   uint32_t tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
   auto tick = [&](int i) {
     if (TIMING) {
@@ -363,18 +378,19 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinB
       for (int i = 0; i < 8; ++i) atomicAdd(a.dbg + role * 8 + i, (unsigned long long)tk[i]);
   };
   using C_ = BwdCfg;
-  constexpr int THREADS = (NWORK + 4) * 32;
+  constexpr int THREADS = BWD_THREADS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = sbase + C_::OFF_BARS;
-  auto tfull = [&](int b) { return bars + 8u * b; };            // T[b] complete                     (commit)
-  auto tempty = [&](int b) { return bars + 8u * (2 + b); };     // workers done with T[b]            (512)
-  auto amfree = [&](int b) { return bars + 8u * (4 + b); };     // T GEMM done reading Amat[b]       (commit)
-  auto d2full = [&](int b) { return bars + 8u * (6 + b); };     // dA^T[b] complete                  (commit)
-  auto d2empty = [&](int b) { return bars + 8u * (8 + b); };    // dA^T[b] drained                   (96)
-  auto gfull = [&](int kb) { return bars + 8u * (10 + kb); };   // G^T k block written               (128)
-  auto gfree = [&](int kb) { return bars + 8u * (14 + kb); };   // dA GEMM done reading the k block  (commit)
-  const uint32_t tmem_slot = bars + 8u * 18;
+  const uint32_t tfull = bars, tempty = bars + 8, amfree = bars + 16;  // T complete (commit) / read (512) / Amat read
+  const uint32_t d2full = bars + 8u * 4;                        // dA complete                       (commit)
+  const uint32_t d2empty = bars + 8u * 6;                       // dA copied to the staging tiles    (96)
+  auto gfull = [&](int kb) { return bars + 8u * (8 + kb); };    // G k block written                 (128)
+  auto gfree = [&](int kb) { return bars + 8u * (12 + kb); };   // dA GEMM done reading the k block  (commit)
+  auto sfull = [&](int st) { return bars + 8u * (16 + st); };   // input stage landed        (tx bytes [+ 32 cp.async])
+  auto sempty = [&](int st) { return bars + 8u * (20 + st); };  // input stage read by the workers   (512)
+  const uint32_t tmem_slot = bars + 8u * 24;
+  static_assert(C_::NSTAGE <= 4, "barrier slots above");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vt = blockIdx.x % NT_V, chunk = blockIdx.x / NT_V;
@@ -388,91 +404,82 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinB
   const int last = a.N - 1;
 
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull(b), 1);
-      mbar_init(tempty(b), NWORK * 32);
-      mbar_init(amfree(b), 1);
-      mbar_init(d2full(b), 1);
-      mbar_init(d2empty(b), 96);
-    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, NWORK * 32);
+    mbar_init(amfree, 1);
+    mbar_init(d2full, 1);
+    mbar_init(d2empty, 96);
     for (int kb = 0; kb < 4; ++kb) {
       mbar_init(gfull(kb), NWORK * 8);
       mbar_init(gfree(kb), 1);
     }
+    for (int st = 0; st < C_::NSTAGE; ++st) {
+      mbar_init(sfull(st), 1);
+      mbar_init(sempty(st), NWORK * 32);
+    }
     fence_barrier_init();
   }
-  constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3;  // warps [W_PROD, W_PROD+3): producers; W_ISSUE: dA GEMM
+  // warps [W_PROD, W_PROD+3): Amat + T GEMM; W_ISSUE: dA GEMM; W_DRAIN, W_DRAIN+1, W_DRAIN+4: accumulator drain;
+  // W_LOAD: input ring; warp NWORK+7 idles (a second drain warp on TMEM lane quarter 0 needs index = 0 mod 4)
+  constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3, W_DRAIN = NWORK + 4, W_LOAD = NWORK + 6;
+  static_assert(W_DRAIN % 4 == 0, "drain warps W_DRAIN, W_DRAIN+4 read TMEM lane quarter 0, W_DRAIN+1 quarter 1");
   if (warp == W_ISSUE) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
-  // zero Amat (pad columns k = 24..31), G^T and its tail
-  for (int i = tid; i < (C_::OFF_BARS - C_::OFF_AM) / 16; i += THREADS)
+  // zero Amat: its pad columns k = 24..31 stay zero for the whole kernel (G is fully rewritten every group)
+  for (int i = tid; i < 2 * AM_BYTES / 16; i += THREADS)
     sts128(sbase + C_::OFF_AM + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32u(tmem_slot);
   if (tid < TILE_V) {
-    // this vertex's 24 weights: tf32 hi / lo into its TMEM lane (A operand of the T GEMM) and into the
-    // [W hi | W lo] B operand of the dA GEMM (row = joint, k = vertex; k block = warp)
-    const int v = v0 + tid;
-    uint32_t h[32], l[32];
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    {
+      // this vertex's 24 weights, tf32 hi / lo, into its TMEM lane: A operand of the T GEMM
+      const int v = v0 + tid;
+      uint32_t h[32], l[32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      float w = k < NJ ? __ldg(a.Wt + (size_t)k * VP + v) : 0.f, hi, lo;
-      tf32_split(w, hi, lo);
-      h[k] = __float_as_uint(hi);
-      l[k] = __float_as_uint(lo);
-      const uint32_t o = sbase + C_::OFF_WD + (uint32_t)(warp * C_::WD_KB_BYTES);
-      if (k < NJ) {
-        sts32(o + kmajor_sw128(k, lane), hi);
-        sts32(o + kmajor_sw128(NJ + k, lane), lo);
+      for (int k = 0; k < 32; ++k) {
+        float w = k < NJ ? __ldg(a.Wt + (size_t)k * VP + v) : 0.f, hi, lo;
+        tf32_split(w, hi, lo);
+        h[k] = __float_as_uint(hi);
+        l[k] = __float_as_uint(lo);
       }
+      tmem_st32(trow + C_::TM_W, h);
+      tmem_st32(trow + C_::TM_W + 32, l);
     }
-    const uint32_t tw = tmem_base + ((uint32_t)(warp * 32) << 16) + C_::TM_W;
-    tmem_st32(tw, h);
-    tmem_st32(tw + 32, l);
+    // A operand of the dA GEMM: lane = joint (warp 0: hi part, warp 1: lo part, warps 2-3: zero), column = vertex
+    const float* wrow = a.Wt + (size_t)min(lane, NJ - 1) * VP + v0;
+#pragma unroll 1
+    for (int c4 = 0; c4 < 4; ++c4) {
+      uint32_t x[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + c4 * 32) + i);
+        const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float hi, lo;
+          tf32_split(ws[e], hi, lo);
+          x[4 * i + e] = (warp < 2 && lane < NJ) ? __float_as_uint(warp == 0 ? hi : lo) : 0u;
+        }
+      }
+      tmem_st32(trow + C_::TM_WT + c4 * 32, x);
+    }
     tmem_st_wait();
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  constexpr uint32_t idesc_t = umma_idesc_tf32(128, NROW, 0, 0);
-  constexpr uint32_t idesc_d48 = umma_idesc_tf32(128, C_::WD_ROWS, 0, 0);
-  constexpr uint32_t idesc_d32 = umma_idesc_tf32(128, 32, 0, 0);
+  constexpr uint32_t idesc = umma_idesc_tf32(128, NROW, 0, 0);
+  constexpr uint32_t idesc_d = umma_idesc_tf32(128, 2 * NROW, 0, 0);
 
   if (warp >= W_PROD && warp < W_ISSUE) {
-    // ------------------------------------------------------------------ producers: Amat, T GEMM issue, dA^T drain
+    // ------------------------------------------------------------------ producers: Amat, T GEMM issue
+    // T of group gi + 1 is issued as soon as every worker has read T of group gi, i.e. a whole group ahead of its use
     const int pt = tid - W_PROD * 32;
     AmatWriter aw;
     aw.init(pt);
-    const int row = (warp & 3) * 32 + lane;  // accumulator lane = (f, r, c); W_PROD % 4 == 0
-    const int rf = row / 12, rq = row % 12;
-    auto drain = [&](int gi) {
-      const int b = gi & 1;
-      mbar_wait(d2full(b), (gi >> 1) & 1);
-      tc_fence_after();
-      uint32_t t[24], u[24];
-      const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C_::TM_D + b * 64;
-      tmem_ld16(ta, t);
-      tmem_ld8(ta + 16, t + 16);
-      tmem_ld16(ta + NJ, u);
-      tmem_ld8(ta + NJ + 16, u + 16);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(d2empty(b));
-      const int n = group_of(gi) * FB + rf;
-      if (n <= last && !(a.ablate & 1)) {
-        float* d = a.dAt + (size_t)n * 288 + rq * 24;
-#pragma unroll
-        for (int j = 0; j < NJ; j += 4)
-          red_add_v4(d + j, __uint_as_float(t[j]) + __uint_as_float(u[j]),
-                     __uint_as_float(t[j + 1]) + __uint_as_float(u[j + 1]),
-                     __uint_as_float(t[j + 2]) + __uint_as_float(u[j + 2]),
-                     __uint_as_float(t[j + 3]) + __uint_as_float(u[j + 3]));
-      }
-    };
-    // The transforms of group gi + 2 are fetched into registers and the T GEMM of group gi + 1 is issued BEFORE this
-    // thread blocks in the drain of group gi: the workers never wait for T.
     float x[FB][3];
     auto fetch = [&](int gi) {
       const int n0 = group_of(gi) * FB;
@@ -483,84 +490,161 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinB
         for (int i = 0; i < 3; ++i) x[s][i] = __ldg(p + 96 * i);
       }
     };
-    auto issue_t = [&](int gi) {
-      const int b = gi & 1;
-      const uint32_t use = gi >> 1;
-      if (use > 0) mbar_wait(amfree(b), (use - 1) & 1);
-      const uint32_t am = sbase + C_::OFF_AM + b * 2 * AM_BYTES;
+    fetch(0);
+    const uint32_t am = sbase + C_::OFF_AM;
+    tprev = (uint32_t)clock();
+    for (int gi = 0; gi < ng; ++gi) {
+      if (gi > 0) mbar_wait(amfree, (gi - 1) & 1);
+      tick(0);
       aw.store(am, x);
       fence_proxy_async_smem();
+      tick(1);
       asm volatile("bar.sync 1, 96;" ::: "memory");
+      tick(2);
+      if (gi + 1 < ng) fetch(gi + 1);
       if (pt == 0) {
-        if (use > 0) mbar_wait(tempty(b), (use - 1) & 1);
+        if (gi > 0) mbar_wait(tempty, (gi - 1) & 1);
+        tick(3);
         tc_fence_after();
-        const uint32_t d = tmem_base + C_::TM_T + b * 128;
+        const uint32_t d = tmem_base + C_::TM_T;
         const uint32_t wh = tmem_base + C_::TM_W, wl = wh + 32;
         const uint64_t mh0 = umma_smem_desc(am, 16, 1024, LAYOUT_SW128);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {  // K = 24 joints = 3 steps of 8
           const uint64_t mh = umma_desc_advance(mh0, j * 32), ml = umma_desc_advance(mh0, AM_BYTES + j * 32);
-          umma_tf32_ts(d, wl + j * 8, mh, idesc_t, j > 0 ? 1u : 0u);
-          umma_tf32_ts(d, wh + j * 8, ml, idesc_t, 1u);
-          umma_tf32_ts(d, wh + j * 8, mh, idesc_t, 1u);
+          umma_tf32_ts(d, wl + j * 8, mh, idesc, j > 0 ? 1u : 0u);
+          umma_tf32_ts(d, wh + j * 8, ml, idesc, 1u);
+          umma_tf32_ts(d, wh + j * 8, mh, idesc, 1u);
         }
-        umma_commit(tfull(b));
-        umma_commit(amfree(b));
+        umma_commit(tfull);
+        umma_commit(amfree);
+        tick(4);
       }
-    };
-    fetch(0);
-    issue_t(0);
-    if (ng > 1) fetch(1);
-    tprev = (uint32_t)clock();
-    for (int gi = 0; gi < ng; ++gi) {
-      if (gi + 1 < ng) {
-        issue_t(gi + 1);
-        tick(0);
-        if (gi + 2 < ng) fetch(gi + 2);
-      }
-      drain(gi);
-      tick(1);
     }
-    tick_flush(1);
+    if (pt == 0) tick_flush(1);
   } else if (warp == W_ISSUE) {
     // ------------------------------------------------------------------ dA GEMM issuer
     if (lane == 0) {
-      const uint64_t gh0 = umma_smem_desc(sbase + C_::OFF_GT, 16, 1024, LAYOUT_SW128);
-      const uint64_t wd0 = umma_smem_desc(sbase + C_::OFF_WD, 16, 1024, LAYOUT_SW128);
+      const uint64_t gh0 = umma_smem_desc(sbase + C_::OFF_G, 16, 1024, LAYOUT_SW128);
+      const uint32_t wt = tmem_base + C_::TM_WT;
       tprev = (uint32_t)clock();
+      // one MMA per k step: N = 192 = [G_hi | G_lo] (a tf32 MMA costs ~96 cycles whatever its N up to ~176 and
+      // ~106 at N = 192 -- measured, tools/ubench/mma_pace.cu -- so the kernel is paced by its MMA COUNT)
+      const uint32_t d = tmem_base + C_::TM_D;
       for (int gi = 0; gi < ng; ++gi) {
-        const int b = gi & 1;
-        const uint32_t use = gi >> 1;
-        const uint32_t d = tmem_base + C_::TM_D + b * 64;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           tick(4 + kb);
           mbar_wait(gfull(kb), gi & 1);
           tick(kb);
-          if (kb == 0 && use > 0) mbar_wait(d2empty(b), (use - 1) & 1);
+          if (kb == 0 && gi > 0) mbar_wait(d2empty, (gi - 1) & 1);
           tc_fence_after();
           if (!(a.ablate & 4))
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t go = kb * C_::GT_KB_BYTES + ks * 32, wo = kb * C_::WD_KB_BYTES + ks * 32;
-            const uint64_t gh = umma_desc_advance(gh0, go), gl = umma_desc_advance(gh0, C_::GT_BYTES + go);
-            const uint64_t wd = umma_desc_advance(wd0, wo);
-            umma_tf32(d, gh, wd, idesc_d48, (kb | ks) ? 1u : 0u);   // [G_hi.W_hi | G_hi.W_lo]
-            // += G_lo.W_hi (N = 32: columns 24..31 also receive G_lo.W_lo of joints 0..7, a valid 4th-order term)
-            umma_tf32(d, gl, wd, idesc_d32, 1u);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32_ts(d, wt + kb * 32 + ks * 8, umma_desc_advance(gh0, kb * C_::GT_KB_BYTES + ks * 32), idesc_d,
+                         (kb | ks) ? 1u : 0u);
           umma_commit(gfree(kb));
         }
-        umma_commit(d2full(b));
+        umma_commit(d2full);
       }
       tick_flush(2);
     }
     __syncwarp();
-  } else {
+  } else if (warp == W_DRAIN || warp == W_DRAIN + 1 || warp == W_DRAIN + 4) {
+    // ------------------------------------------------------------------ accumulator drain
+    // The accumulator is single buffered (tensor memory is full), so it is released as soon as it has been COPIED:
+    // three warps move 96 columns each into the staging tiles, then add the three partial sums in place and ONE
+    // thread hands the group's 9 KB slab to the bulk-reduce engine (cp.reduce.async.bulk .add.f32 into global dA):
+    // no per-thread atomics, the LSU never sees the 54-way accumulation over vertex tiles.
+    const int dw = warp == W_DRAIN ? 0 : (warp == W_DRAIN + 4 ? 1 : 2);  // staging tile
+    const int dt = dw * 32 + lane;
+    const uint32_t ta = tmem_base + ((uint32_t)(dw == 2 ? 32 : 0) << 16) + C_::TM_D + (dw == 1 ? NROW : 0);
+    const uint32_t stg0 = sbase + C_::OFF_STG;
+    const uint32_t stg = stg0 + dw * C_::STG_BYTES + lane * 48;
+    tprev = (uint32_t)clock();
+    for (int gi = 0; gi < ng; ++gi) {
+      mbar_wait(d2full, gi & 1);
+      tick(0);
+      tc_fence_after();
+      if (dt == 0) bulk_wait_read0();  // the previous slab has left shared memory (tile 0 is rewritten by this warp)
+      __syncwarp();
+      tick(1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // four frames = 48 accumulator columns per batch of loads
+        uint32_t t[48];
+        tmem_ld16(ta + h * 48, t);
+        tmem_ld16(ta + h * 48 + 16, t + 16);
+        tmem_ld16(ta + h * 48 + 32, t + 32);
+        tmem_ld_wait();
+        if (lane < NJ) {
+#pragma unroll
+          for (int q = 0; q < 12; ++q)
+            sts128(stg + (h * 4 + q / 3) * 1152 + (q % 3) * 16,
+                   make_float4(__uint_as_float(t[4 * q]), __uint_as_float(t[4 * q + 1]), __uint_as_float(t[4 * q + 2]),
+                               __uint_as_float(t[4 * q + 3])));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(d2empty);
+      tick(2);
+      asm volatile("bar.sync 2, 96;" ::: "memory");  // staging tiles written
+#pragma unroll
+      for (int k = 0; k < FB * 72 / 96; ++k) {
+        const uint32_t so = stg0 + (dt + 96 * k) * 16;
+        const float4 x = lds128(so), y = lds128(so + C_::STG_BYTES), z = lds128(so + 2 * C_::STG_BYTES);
+        sts128(so, make_float4(x.x + y.x + z.x, x.y + y.y + z.y, x.z + y.z + z.z, x.w + y.w + z.w));
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 96;" ::: "memory");  // slab complete (and tiles 1, 2 free again)
+      if (dt == 0 && !(a.ablate & 1)) {
+        const int n0 = group_of(gi) * FB;
+        bulk_reduce_add_f32(a.dA + (size_t)n0 * 288, stg0, (uint32_t)min(FB, a.N - n0) * 1152u);
+        bulk_commit();
+      }
+      tick(3);
+    }
+    if (dt == 0) bulk_wait_all();
+    if (dw == 0) tick_flush(3);
+  } else if (warp == W_LOAD) {
+    // ------------------------------------------------------------------ input loader
+    for (int gi = 0; gi < ng; ++gi) {
+      const int st = gi % C_::NSTAGE;
+      const uint32_t use = gi / C_::NSTAGE;
+      if (use > 0) mbar_wait(sempty(st), (use - 1) & 1);
+      const uint32_t sa = sbase + C_::OFF_ST + st * C_::ST_BYTES;
+      const int n0 = group_of(gi) * FB;
+      if (a.ablate & 16) {
+        if (lane == 0) mbar_arrive(sfull(st));
+      } else {
+        // lanes 0..23: pose offsets of (frame, component) = (lane / 3, lane % 3); lanes 24..31: dV of frame lane - 24
+        const void* src;
+        uint32_t dst, bytes;
+        if (lane < 24) {
+          src = a.PO + (size_t)min(n0 + lane / 3, last) * (3 * VP) + (lane % 3) * VP + v0;
+          dst = sa + lane * (TILE_V * 4);
+          bytes = TILE_V * 4;
+        } else {
+          const int f = lane - 24, n = min(n0 + f, last), odd = n & 1;
+          src = reinterpret_cast<const char*>(a.dV + (size_t)n * (NV * 3)) + v0 * 12 - 8 * odd;
+          dst = sa + C_::ST_PO_BYTES + f * C_::DV_SLOT;
+          // last tile: the frame ends after 106 vertices (1272 bytes); an even frame is cut to a 16-byte multiple
+          // and the worker of the last vertex fetches its y, z itself
+          bytes = vt == NT_V - 1 ? (odd ? 1280u : 1264u) : (odd ? TILE_V * 12 + 16 : TILE_V * 12);
+          if (!HAS_DV) bytes = 0;
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbar_arrive_expect_tx(sfull(st), total);
+        __syncwarp();
+        if (bytes) bulk_g2s(dst, src, bytes, sfull(st));
+      }
+    }
+  } else if (warp < NWORK) {
     // ------------------------------------------------------------------ workers: four threads per vertex
     // warp = 4 * (frame pair) + (TMEM lane quarter): the four warps of a quarter share one warp scheduler and one
-    // G^T k block and take two frames of the group each, so their barrier / TMEM / HBM latencies overlap
+    // G k block and take two frames of the group each, so their barrier / TMEM latencies overlap
     constexpr int FH = FB * 4 / NWORK;  // frames of the group per worker warp
+    static_assert(FH == 2, "two frames per worker warp");
     const int wq = warp & 3, half = warp >> 2;
     const int v = v0 + wq * 32 + lane;
     const bool real = v < NV;
@@ -568,53 +652,57 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinB
 #pragma unroll
     for (int c = 0; c < 3; ++c) bs[c] = __ldg(a.base + c * VP + v);
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    // G^T addresses: row = half*48 + f*12 + q (q = r*4 + c), k = lane.  The swizzle phase row & 7 = ((f&1)*4 + q) & 7
+    // G addresses: row = half*24 + f*12 + q (q = r*4 + c), k = lane.  The swizzle phase row & 7 = ((f&1)*4 + q) & 7
     // is a compile-time constant per (f, q): eight lane-dependent offsets cover every store
-    const uint32_t gt = sbase + C_::OFF_GT + wq * C_::GT_KB_BYTES + half * (FH * 12 * 128) + ((lane & 3) << 2);
+    const uint32_t gt = sbase + C_::OFF_G + wq * C_::GT_KB_BYTES + half * (FH * 12 * 128) + ((lane & 3) << 2);
     uint32_t xo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) xo[i] = gt + ((((lane >> 2) ^ i) & 7) << 4);
     const unsigned lbit = 1u << lane;
     const float sp = a.sign_scale, sn = -a.sign_scale;
 
-    float pA[FH][3], dA_[FH][3], pB[FH][3], dB_[FH][3];
-    uint32_t sA = 0u, sB = 0u;  // this half's 24 sign words, one per lane
-    auto load_in = [&](int gi, float (&p)[FH][3], float (&d)[FH][3], uint32_t& w) {
+    uint32_t sA = 0u, sB = 0u;  // this half's 12 sign words (two frames), one per lane, prefetched one group ahead
+    auto load_signs = [&](int gi, uint32_t& w) {
+      if (!HAS_SIGNS) return;
       const int n0 = group_of(gi < ng ? gi : ng - 1) * FB + half * FH;
-      if (a.ablate & 16) return;
-      if (HAS_SIGNS) {
-        const int fc = lane >> 1;  // word (f*3 + c)*2 + {pos, neg}
-        const int n = min(n0 + fc / 3, last);
-        w = lane < FH * 6 ? __ldg(a.signs + (((size_t)n * 3 + fc % 3) * 2 + (lane & 1)) * (VP / 32) + (v >> 5)) : 0u;
-      }
+      const int fc = lane >> 1;  // word (f*3 + c)*2 + {pos, neg}
+      const int n = min(n0 + fc / 3, last);
+      w = lane < FH * 6 ? __ldg(a.signs + (((size_t)n * 3 + fc % 3) * 2 + (lane & 1)) * (VP / 32) + (v >> 5)) : 0u;
+    };
+    const uint32_t st_po = sbase + C_::OFF_ST + (half * FH * 3) * (TILE_V * 4) + (wq * 32 + lane) * 4;
+    const uint32_t st_dv = sbase + C_::OFF_ST + C_::ST_PO_BYTES + (half * FH) * C_::DV_SLOT + (wq * 32 + lane) * 12;
+    auto body = [&](int gi, uint32_t sw, uint32_t& swn) {
+      const int n0 = group_of(gi) * FB + half * FH;
+      load_signs(gi + 1, swn);
+      // ---- this group's inputs from the ring
+      float po[FH][3], dv[FH][3];
+      {
+        const int st = gi % C_::NSTAGE;
+        mbar_wait(sfull(st), (gi / C_::NSTAGE) & 1);
+        const uint32_t so = st * C_::ST_BYTES;
 #pragma unroll
-      for (int f = 0; f < FH; ++f) {
-        const int n = min(n0 + f, last);
-        const float* pp = a.PO + (size_t)n * (3 * VP) + v;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) p[f][c] = __ldcs(pp + c * VP);
-        if (HAS_DV) {
-          const float* dp = a.dV + ((size_t)n * NV + (real ? v : NV - 1)) * 3;
+        for (int f = 0; f < FH; ++f)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float x = __ldcs(dp + c);
-            d[f][c] = real ? x : 0.f;
+            po[f][c] = lds32(st_po + so + (f * 3 + c) * (TILE_V * 4));
+            if (HAS_DV) {
+              const int n = min(n0 + f, last);
+              float x = lds32(st_dv + so + f * C_::DV_SLOT + 8 * (n & 1) + c * 4);
+              if (v == NV - 1 && !(n & 1) && c > 0) x = __ldg(a.dV + ((size_t)n * NV + v) * 3 + c);  // see the loader
+              dv[f][c] = real ? x : 0.f;
+            } else {
+              dv[f][c] = 0.f;
+            }
           }
+        if (TIMING) {  // force the arrival
+          float acc = 0.f;
+          for (int f = 0; f < FH; ++f)
+            for (int c = 0; c < 3; ++c) acc += po[f][c] + dv[f][c];
+          if (acc == 1.2345e-30f) tk[7] += 1;
         }
+        mbar_arrive(sempty(st));
       }
-    };
-    auto body = [&](int gi, float (&po)[FH][3], float (&dv)[FH][3], uint32_t sw, float (&pn)[FH][3],
-                    float (&dn)[FH][3], uint32_t& swn) {
-      const int b = gi & 1;
-      const int n0 = group_of(gi) * FB + half * FH;
-      if (TIMING) {  // force the arrival of this group's inputs (prefetched during the previous group)
-        float acc = 0.f;
-        for (int f = 0; f < FH; ++f)
-          for (int c = 0; c < 3; ++c) acc += po[f][c] + (HAS_DV ? dv[f][c] : 0.f);
-        if (acc == 1.2345e-30f) tk[7] += 1;
-        tick(0);
-      }
-      load_in(gi + 1, pn, dn, swn);
+      tick(0);
       // ---- upstream gradient of the vertex in each frame
       if (HAS_SIGNS) {
 #pragma unroll
@@ -624,28 +712,22 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinB
             const uint32_t pm = __shfl_sync(0xffffffffu, sw, (f * 3 + c) * 2);
             const uint32_t nm = __shfl_sync(0xffffffffu, sw, (f * 3 + c) * 2 + 1);
             const float s = (pm & lbit) ? sp : ((nm & lbit) ? sn : 0.f);
-            dv[f][c] = HAS_DV ? dv[f][c] + s : s;
+            dv[f][c] += s;
           }
       }
-      // ---- dPO = R^T dv from the T rows in TMEM (all of this half's rows in one batch of loads)
+      // ---- dPO = R^T dv from the T rows in TMEM
       tick(1);
-      mbar_wait(tfull(b), (gi >> 1) & 1);
+      mbar_wait(tfull, gi & 1);
       tick(2);
       tc_fence_after();
       uint32_t t[FH * 12];
-      const uint32_t ta = tmem_base + lane_addr + C_::TM_T + b * 128 + half * (FH * 12);
-      static_assert(FH == 2 || FH == 4, "TMEM loads below fetch 24 or 48 columns");
+      const uint32_t ta = tmem_base + lane_addr + C_::TM_T + half * (FH * 12);
       tmem_ld16(ta, t);
-      if (FH == 2) {
-        tmem_ld8(ta + 16, t + 16);
-      } else {
-        tmem_ld16(ta + 16, t + 16);
-        tmem_ld16(ta + 32, t + 32);
-      }
+      tmem_ld8(ta + 16, t + 16);
       tmem_ld_wait();
       tick(3);
       tc_fence_before();
-      mbar_arrive(tempty(b));
+      mbar_arrive(tempty);
       {
         float* d = a.dPO + (size_t)n0 * (3 * VP) + v;
 #pragma unroll
@@ -659,7 +741,7 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinB
           }
         }
       }
-      // ---- G^T for the dA GEMM (the previous group's MMAs over this k block must have finished reading it)
+      // ---- G for the dA GEMM (the previous group's MMAs over this k block must have finished reading it)
       tick(4);
       if (gi > 0) mbar_wait(gfree(wq), (gi - 1) & 1);
       tick(5);
@@ -675,18 +757,18 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 1) k_skin_tc_bwd(const SkinB
             const float g = c < 3 ? dv[f][r] * ph[c] : dv[f][r];
             const uint32_t off = xo[((f & 1) * 4 + q) & 7] + (f * 12 + q) * 128;
             sts32(off, g);
-            sts32(off + C_::GT_BYTES, g - trunc_tf32(g));
+            sts32(off + C_::GT_LO, g - trunc_tf32(g));
           }
       }
       fence_proxy_async_smem();
       mbar_arrive(gfull(wq));
       tick(6);
     };
-    load_in(0, pA, dA_, sA);
+    load_signs(0, sA);
     tprev = (uint32_t)clock();
     for (int gi = 0; gi < ng; gi += 2) {
-      body(gi, pA, dA_, sA, pB, dB_, sB);
-      if (gi + 1 < ng) body(gi + 1, pB, dB_, sB, pA, dA_, sA);
+      body(gi, sA, sB);
+      if (gi + 1 < ng) body(gi + 1, sB, sA);
     }
     tick_flush(0);
   }
@@ -729,37 +811,39 @@ int launch_fwd(const SkinArgs& a, cudaStream_t s) {
   NB_LAUNCH_CHECK("skin_tc_fwd");
 }
 
-template <bool HAS_DV, bool HAS_SIGNS, int NWORK>
-int launch_bwd_n(const SkinBwdArgs& a, cudaStream_t s) {
+template <bool HAS_DV, bool HAS_SIGNS>
+int launch_bwd_plain(const SkinBwdArgs& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<HAS_DV, HAS_SIGNS, NWORK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<HAS_DV, HAS_SIGNS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BwdCfg::SMEM_BYTES));
     configured = true;
   }
-  k_skin_tc_bwd<HAS_DV, HAS_SIGNS, NWORK><<<NT_V * a.nchunks, (NWORK + 4) * 32, BwdCfg::SMEM_BYTES, s>>>(a);
+  k_skin_tc_bwd<HAS_DV, HAS_SIGNS><<<NT_V * a.nchunks, BWD_THREADS, BwdCfg::SMEM_BYTES, s>>>(a);
   NB_LAUNCH_CHECK("skin_tc_bwd");
 }
 
 // NEMO_B200_SKIN_TIMING=1 (debug): run the instrumented dV kernel, synchronise and print the phase counters
 int launch_bwd_timing(SkinBwdArgs a, cudaStream_t s) {
   static unsigned long long* dbg = nullptr;
-  if (!dbg) NB_CUDA(cudaMalloc(&dbg, 24 * sizeof(unsigned long long)));
-  NB_CUDA(cudaMemsetAsync(dbg, 0, 24 * sizeof(unsigned long long), s));
+  if (!dbg) NB_CUDA(cudaMalloc(&dbg, 40 * sizeof(unsigned long long)));
+  NB_CUDA(cudaMemsetAsync(dbg, 0, 40 * sizeof(unsigned long long), s));
   a.dbg = dbg;
-  NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<true, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                BwdCfg::SMEM_BYTES));
-  k_skin_tc_bwd<true, false, 8, true><<<NT_V * a.nchunks, 12 * 32, BwdCfg::SMEM_BYTES, s>>>(a);
+  k_skin_tc_bwd<true, false, true><<<NT_V * a.nchunks, BWD_THREADS, BwdCfg::SMEM_BYTES, s>>>(a);
   NB_CUDA(cudaStreamSynchronize(s));
-  unsigned long long h[24];
+  unsigned long long h[40];
   NB_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
   const double groups = (double)NT_V * cdiv(a.N, FB);
-  static const char* names[3][8] = {
-      {"inputs arrive", "issue prefetch+signs", "wait tfull", "tmem ld", "dPO", "wait gfree", "G phase", "-"},
-      {"issue_t", "fetch+drain", "-", "-", "-", "-", "-", "-"},
-      {"wait gfull0", "wait gfull1", "wait gfull2", "wait gfull3", "mma0", "mma1", "mma2", "mma3"}};
-  const double per[3] = {8.0, 3.0, 1.0};  // warps per role
-  for (int r = 0; r < 3; ++r) {
+  static const char* names[5][8] = {
+      {"inputs (ring)", "signs", "wait tfull", "tmem ld", "dPO", "wait gfree", "G phase", "-"},
+      {"wait amfree", "Amat store", "bar", "fetch + wait tempty", "T mma issue", "-", "-", "-"},
+      {"wait gfull0", "wait gfull1", "wait gfull2", "wait gfull3", "mma0", "mma1", "mma2", "mma3"},
+      {"wait d2full", "wait slab read", "copy", "sum + bulk reduce", "-", "-", "-", "-"},
+      {"-", "-", "-", "-", "-", "-", "-", "-"}};
+  const double per[5] = {(double)NWORK, 1.0, 1.0, 1.0, 1.0};  // warps per role
+  for (int r = 0; r < 5; ++r) {
     fprintf(stderr, "[skin_bwd timing] role %d:", r);
     for (int i = 0; i < 8; ++i)
       if (names[r][i][0] != '-') fprintf(stderr, "  %s %.0f", names[r][i], (double)h[r * 8 + i] / groups / per[r]);
@@ -772,8 +856,7 @@ template <bool HAS_DV, bool HAS_SIGNS>
 int launch_bwd(const SkinBwdArgs& a, cudaStream_t s) {
   static const int timing = [] { const char* e = getenv("NEMO_B200_SKIN_TIMING"); return e ? atoi(e) : 0; }();
   if (timing && HAS_DV && !HAS_SIGNS) return launch_bwd_timing(a, s);
-  static const int nwork = [] { const char* e = getenv("NEMO_B200_SKIN_BWD_WARPS"); return e ? atoi(e) : 16; }();
-  return nwork == 8 ? launch_bwd_n<HAS_DV, HAS_SIGNS, 8>(a, s) : launch_bwd_n<HAS_DV, HAS_SIGNS, 16>(a, s);
+  return launch_bwd_plain<HAS_DV, HAS_SIGNS>(a, s);
 }
 
 }  // namespace
@@ -801,18 +884,18 @@ extern "C" int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const 
 }
 
 extern "C" int nemo_b200_skin_bwd(const float* A, const float* PO, const float* base, const float* Wt, const float* dV,
-                                  const uint32_t* signs, float sign_scale, float* dPO, float* dAt, int N,
+                                  const uint32_t* signs, float sign_scale, float* dPO, float* dA, int N,
                                   void* stream) {
   if (N == 0) return 0;
-  NB_REQUIRE(A && PO && base && Wt && dPO && dAt && (dV || signs) && N >= 0, "skin_bwd: bad args");
+  NB_REQUIRE(A && PO && base && Wt && dPO && dA && (dV || signs) && N >= 0, "skin_bwd: bad args");
   cudaStream_t s = S(stream);
   SkinBwdArgs a{};
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.dV = dV; a.signs = signs;
-  a.sign_scale = sign_scale; a.dPO = dPO; a.dAt = dAt; a.N = N;
+  a.sign_scale = sign_scale; a.dPO = dPO; a.dA = dA; a.N = N;
   chunking(N, FB, a.groups_per_chunk, a.nchunks);
   static const int abl = [] { const char* e = getenv("NEMO_B200_SKIN_ABLATE"); return e ? atoi(e) : 0; }();
   a.ablate = abl;
-  NB_CUDA(cudaMemsetAsync(dAt, 0, sizeof(float) * (size_t)N * 288, s));  // vertex tiles accumulate with reductions
+  NB_CUDA(cudaMemsetAsync(dA, 0, sizeof(float) * (size_t)N * 288, s));  // vertex tiles accumulate with reductions
   if (dV && signs) return launch_bwd<true, true>(a, s);
   if (dV) return launch_bwd<true, false>(a, s);
   return launch_bwd<false, true>(a, s);

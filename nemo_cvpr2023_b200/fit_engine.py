@@ -232,7 +232,7 @@ class FitEngine:
             E1=z(N, H_VP), head=z(N, 2 * L_VP), dhead=z(N, 2 * L_VP), D1=z(N, H_VP), D2=z(N, H_VP), D3=z(N, 126),
             Rdec=z(N * 21, 9), recon=z(N, 69), signs=torch.zeros(N, 3, 2, VP // 32, dtype=torch.int32, device=d),
             ll=z(N), acc=z(8), terms=z(8), wts=z(8), total=z(1),
-            d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dAt=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
+            d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dAs=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
             dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, LDY), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.ldx),
             dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dbase=z(3 * VP),
             base=z(3, VP), J=z(72), vi=torch.zeros(N, dtype=torch.long, device=d),
@@ -405,8 +405,8 @@ class FitEngine:
                 gemm(w['dE1'], vp['W1e'], w['d_aa'], N, 72, H_VP, H_VP, 72, 72, accumulate=True)
             if full and w_vp:
                 lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, None, w['signs'], ls * w_vp / (N * NV * 3.0),
-                             w['dPO'], w['dAt'], N)
-                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, None, w['dAt'], None, w['dR_o'], w['dJ'].zero_(), N)
+                             w['dPO'], w['dAs'], N)
+                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, w['dAs'], None, None, w['dR_o'], w['dJ'].zero_(), N)
                 gemm(w['dPO'], C.PD, w['dR_o'].view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
                      accumulate=True)
                 if self.compute_betas_grad:

@@ -435,16 +435,17 @@ class _LBS(torch.autograd.Function):
         dV = None if dV is None or dV.numel() == 0 or PO is None else _f32c(dV)
         dJX = None if dJX is None or dJX.numel() == 0 or Z is None else _f32c(dJX)
         dJP = None if dJP is None else _f32c(dJP)
-        dA = dZ = dPO = dAt = None
+        dA = dZ = dPO = None
         if dJX is not None:
             dA, dZ = _new((N, 24, 12), rot), _new((N, ldz), rot)
             lib.readout_bwd(A, Z, ldz, ro['Wp'], ro['np'], ro['Sj'], ro['nx'], dJX, dA, 0, dZ, N)
         if dV is not None:
-            dPO, dAt = _new((N, 3 * VP), rot), _new((N, 12, 24), rot)
-            lib.skin_bwd(A, PO, base, C.Wt, dV, None, 0.0, dPO, dAt, N)
+            dPO, dAs = _new((N, 3 * VP), rot), _new((N, 24, 12), rot)
+            lib.skin_bwd(A, PO, base, C.Wt, dV, None, 0.0, dPO, dAs, N)
+            dA = dAs if dA is None else dA.add_(dAs)
         dR = _new((N, 24, 9), rot)
         dJ = _new((N, 72), rot) if ctx.per_frame else torch.zeros(72, device=rot.device)
-        lib.chain_bwd(rot, J, ctx.js, C.parents, dA, dAt, dJP, dR, dJ, N)
+        lib.chain_bwd(rot, J, ctx.js, C.parents, dA, None, dJP, dR, dJ, N)
         # dR[:, 1:] += d(pose feature), written in place through the leading dimension (pose_feature backward)
         if dPO is not None:
             gemm(dPO, C.PD, dR.view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True, accumulate=True)

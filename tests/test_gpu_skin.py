@@ -50,21 +50,21 @@ def test_skin_forward_and_backward_ragged(ctx, N):
     lib.skin_fwd(A32, PO32, C.vt, C.Wt, V, N)
     ref, p, T = _ref_skin(A, PO, sm)
     assert_abs(V.double().cpu().numpy(), ref, TOL_VERT_ABS, 'vertices N=%d' % N)
-    # backward: dPO = R^T dv (planar), dAt[n][r*4+c][j] = sum_v W[v,j] dv[n,v,r] [p;1][c]
+    # backward: dPO = R^T dv (planar), dA[n][j][r*4+c] = sum_v W[v,j] dv[n,v,r] [p;1][c]
     r = np.random.RandomState(100 + N)
     dV32 = g32(r.standard_normal((N, 6890, 3)))
     dV = dV32.double().cpu().numpy()
     dPO = torch.full((N, 3 * 6912), float('nan'), device=DEV)
-    dAt = torch.full((N, 12, 24), float('nan'), device=DEV)
-    lib.skin_bwd(A32, PO32, C.vt, C.Wt, dV32, None, 0.0, dPO, dAt, N)
+    dAs = torch.full((N, 24, 12), float('nan'), device=DEV)
+    lib.skin_bwd(A32, PO32, C.vt, C.Wt, dV32, None, 0.0, dPO, dAs, N)
     dPO_ref = np.einsum('nvrc,nvr->ncv', T[..., :3], dV)
     got = dPO.double().cpu().numpy().reshape(N, 3, 6912)
     assert_grad(got[:, :, :6890], dPO_ref, TOL_GRAD_REL, 'dPO N=%d' % N)
     assert np.all(got[:, :, 6890:] == 0), 'pad vertices must get a zero gradient'
     ph = np.concatenate([p, np.ones_like(p[..., :1])], -1)
     W = np.asarray(sm['lbs_weights'], np.float64)
-    dA_ref = np.einsum('vj,nvr,nvc->nrcj', W, dV, ph).reshape(N, 12, 24)
-    assert_grad(dAt.double().cpu().numpy(), dA_ref, TOL_GRAD_REL, 'dAt N=%d' % N)
+    dA_ref = np.einsum('vj,nvr,nvc->njrc', W, dV, ph).reshape(N, 24, 12)
+    assert_grad(dAs.double().cpu().numpy(), dA_ref, TOL_GRAD_REL, 'dA N=%d' % N)
 
 
 @pytest.mark.parametrize('N', [1, 5, 36, 131])
@@ -84,14 +84,14 @@ def test_fused_l1_and_sign_backward(ctx, N):
     assert abs(float(l1) - ref) <= 1e-5 * ref, (float(l1), ref)
     scale = 0.37
     dPO = torch.empty(N, 3 * 6912, device=DEV)
-    dAt = torch.empty(N, 12, 24, device=DEV)
-    lib.skin_bwd(a32, p32, C.vt, C.Wt, None, signs, scale, dPO, dAt, N)
+    dAs = torch.empty(N, 24, 12, device=DEV)
+    lib.skin_bwd(a32, p32, C.vt, C.Wt, None, signs, scale, dPO, dAs, N)
     dV = scale * np.sign(va - vb)
     dPO_ref = np.einsum('nvrc,nvr->ncv', T[..., :3], dV)
     assert_grad(dPO.double().cpu().numpy().reshape(N, 3, 6912)[:, :, :6890], dPO_ref, TOL_GRAD_REL, 'dPO (signs)')
     ph = np.concatenate([p, np.ones_like(p[..., :1])], -1)
-    dA_ref = np.einsum('vj,nvr,nvc->nrcj', np.asarray(sm['lbs_weights'], np.float64), dV, ph).reshape(N, 12, 24)
-    assert_grad(dAt.double().cpu().numpy(), dA_ref, TOL_GRAD_REL, 'dAt (signs)')
+    dA_ref = np.einsum('vj,nvr,nvc->njrc', np.asarray(sm['lbs_weights'], np.float64), dV, ph).reshape(N, 24, 12)
+    assert_grad(dAs.double().cpu().numpy(), dA_ref, TOL_GRAD_REL, 'dA (signs)')
 
 
 @pytest.mark.parametrize('N', [1, 33])

@@ -20,7 +20,7 @@ PO = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
 PO2 = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
 dV = torch.randn(N, Fn.NV, 3, device=dev, generator=g)
 V = torch.empty(N, Fn.NV, 3, device=dev)
-dPO, dAt = torch.empty_like(PO), torch.empty(N, 12, 24, device=dev)
+dPO, dAs = torch.empty_like(PO), torch.empty(N, 24, 12, device=dev)
 signs = torch.zeros(N, 3, 2, Fn.VP // 32, dtype=torch.int32, device=dev)
 l1 = torch.zeros(1, device=dev)
 ro = C.readout
@@ -58,8 +58,8 @@ def readout_fwd():
 cases = [
     ('fwd  V', 2, lambda: lib.skin_fwd(A, PO, C.vt, C.Wt, V, N)),
     ('l1   two meshes + sign bits', 2, lambda: lib.skin_l1_fwd(A, PO, A2, PO2, C.vt, C.Wt, signs, l1, N)),
-    ('bwd  dV -> dPO, dAt', 3, lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAt, N)),
-    ('bwd  signs -> dPO, dAt', 2, lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, None, signs, 1e-3, dPO, dAt, N)),
+    ('bwd  dV -> dPO, dA', 3, lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAs, N)),
+    ('bwd  signs -> dPO, dA', 2, lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, None, signs, 1e-3, dPO, dAs, N)),
     ('read-outs fwd (np=%d nx=%d): Z GEMM + kernel' % (ro['np'], ro['nx']), 0, readout_fwd),
     ('read-outs bwd: dA, dZ', 0,
      lambda: lib.readout_bwd(A, Z, ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], dJX, dA, 0, dZ, N)),
