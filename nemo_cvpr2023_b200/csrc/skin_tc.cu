@@ -322,13 +322,13 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
 struct BwdCfg {
   static constexpr int GT_LO = NROW * 128;               // rows 96..191 of a k block: the lo part
   static constexpr int GT_KB_BYTES = 2 * NROW * 128;     // one 32-vertex k block of G: [hi | lo] = 192 rows x 128 B
-  static constexpr int OFF_AM = 0;                       // [hi][lo] x 12 KB
-  static constexpr int OFF_G = OFF_AM + 2 * AM_BYTES;    // 4 k blocks x 24 KB
+  static constexpr int OFF_AM = 0;                       // 2 buffers x [hi][lo] x 12 KB
+  static constexpr int OFF_G = OFF_AM + 4 * AM_BYTES;    // 4 k blocks x 24 KB
   // input ring: the pose offsets (planar: 3 x 512 bytes per frame) and the upstream vertex gradient (interleaved xyz:
   // 1536 bytes per frame) of NSTAGE frame groups are in flight as 32 bulk async copies per group, one per lane of the
   // loader warp -- the HBM latency is covered by the ring, not by registers.  The frame stride of dV (82 680 bytes) is
   // only 8-byte aligned: an odd frame is copied from 8 bytes earlier (+16 bytes) and read at an 8-byte offset.
-  static constexpr int NSTAGE = 3;
+  static constexpr int NSTAGE = 2;
   static constexpr int ST_PO_BYTES = FB * 3 * TILE_V * 4;
   static constexpr int DV_SLOT = TILE_V * 12 + 16;
   static constexpr int ST_DV_BYTES = FB * DV_SLOT;
@@ -382,7 +382,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = sbase + C_::OFF_BARS;
-  const uint32_t tfull = bars, tempty = bars + 8, amfree = bars + 16;  // T complete (commit) / read (512) / Amat read
+  const uint32_t tfull = bars, tempty = bars + 8;               // T complete (commit) / read by the workers (512)
+  auto amfree = [&](int b) { return bars + 8u * (2 + b); };     // T GEMM done reading Amat[b]       (commit)
+  auto amfull = [&](int b) { return bars + 8u * (26 + b); };    // Amat[b] written                   (96)
   const uint32_t d2full = bars + 8u * 4;                        // dA complete                       (commit)
   const uint32_t d2empty = bars + 8u * 6;                       // dA copied to the staging tiles    (96)
   auto gfull = [&](int kb) { return bars + 8u * (8 + kb); };    // G k block written                 (128)
@@ -406,7 +408,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   if (tid == 0) {
     mbar_init(tfull, 1);
     mbar_init(tempty, NWORK * 32);
-    mbar_init(amfree, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(amfree(b), 1);
+      mbar_init(amfull(b), 96);
+    }
     mbar_init(d2full, 1);
     mbar_init(d2empty, 96);
     for (int kb = 0; kb < 4; ++kb) {
@@ -419,13 +424,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
     }
     fence_barrier_init();
   }
-  // warps [W_PROD, W_PROD+3): Amat + T GEMM; W_ISSUE: dA GEMM; W_DRAIN, W_DRAIN+1, W_DRAIN+4: accumulator drain;
-  // W_LOAD: input ring; warp NWORK+7 idles (a second drain warp on TMEM lane quarter 0 needs index = 0 mod 4)
-  constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3, W_DRAIN = NWORK + 4, W_LOAD = NWORK + 6;
+  // warps [W_PROD, W_PROD+3): Amat writers; W_ISSUE: dA GEMM; W_DRAIN, W_DRAIN+1, W_DRAIN+4: accumulator drain
+  // (TMEM lane quarters 0, 1, 0); W_LOAD: input ring; W_TISSUE: T GEMM
+  constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3, W_DRAIN = NWORK + 4, W_LOAD = NWORK + 6, W_TISSUE = NWORK + 7;
   static_assert(W_DRAIN % 4 == 0, "drain warps W_DRAIN, W_DRAIN+4 read TMEM lane quarter 0, W_DRAIN+1 quarter 1");
   if (warp == W_ISSUE) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   // zero Amat: its pad columns k = 24..31 stay zero for the whole kernel (G is fully rewritten every group)
-  for (int i = tid; i < 2 * AM_BYTES / 16; i += THREADS)
+  for (int i = tid; i < 4 * AM_BYTES / 16; i += THREADS)
     sts128(sbase + C_::OFF_AM + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   tc_fence_before();
   __syncthreads();
@@ -475,8 +480,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   constexpr uint32_t idesc_d = umma_idesc_tf32(128, 2 * NROW, 0, 0);
 
   if (warp >= W_PROD && warp < W_ISSUE) {
-    // ------------------------------------------------------------------ producers: Amat, T GEMM issue
-    // T of group gi + 1 is issued as soon as every worker has read T of group gi, i.e. a whole group ahead of its use
+    // ------------------------------------------------------------------ Amat writers (double buffered)
     const int pt = tid - W_PROD * 32;
     AmatWriter aw;
     aw.init(pt);
@@ -491,24 +495,31 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
       }
     };
     fetch(0);
-    const uint32_t am = sbase + C_::OFF_AM;
     tprev = (uint32_t)clock();
     for (int gi = 0; gi < ng; ++gi) {
-      if (gi > 0) mbar_wait(amfree, (gi - 1) & 1);
+      const int b = gi & 1;
+      if (gi > 1) mbar_wait(amfree(b), ((gi >> 1) - 1) & 1);
       tick(0);
-      aw.store(am, x);
+      aw.store(sbase + C_::OFF_AM + b * 2 * AM_BYTES, x);
       fence_proxy_async_smem();
+      mbar_arrive(amfull(b));
       tick(1);
-      asm volatile("bar.sync 1, 96;" ::: "memory");
-      tick(2);
       if (gi + 1 < ng) fetch(gi + 1);
-      if (pt == 0) {
+      tick(2);
+    }
+    if (pt == 0) tick_flush(1);
+  } else if (warp == W_TISSUE) {
+    // ------------------------------------------------------------------ T GEMM issuer
+    // T of group gi + 1 is issued as soon as every worker has read T of group gi, i.e. a whole group ahead of its use
+    if (lane == 0) {
+      const uint32_t d = tmem_base + C_::TM_T;
+      const uint32_t wh = tmem_base + C_::TM_W, wl = wh + 32;
+      for (int gi = 0; gi < ng; ++gi) {
+        const int b = gi & 1;
+        mbar_wait(amfull(b), (gi >> 1) & 1);
         if (gi > 0) mbar_wait(tempty, (gi - 1) & 1);
-        tick(3);
         tc_fence_after();
-        const uint32_t d = tmem_base + C_::TM_T;
-        const uint32_t wh = tmem_base + C_::TM_W, wl = wh + 32;
-        const uint64_t mh0 = umma_smem_desc(am, 16, 1024, LAYOUT_SW128);
+        const uint64_t mh0 = umma_smem_desc(sbase + C_::OFF_AM + b * 2 * AM_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {  // K = 24 joints = 3 steps of 8
           const uint64_t mh = umma_desc_advance(mh0, j * 32), ml = umma_desc_advance(mh0, AM_BYTES + j * 32);
@@ -517,11 +528,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
           umma_tf32_ts(d, wh + j * 8, mh, idesc, 1u);
         }
         umma_commit(tfull);
-        umma_commit(amfree);
-        tick(4);
+        umma_commit(amfree(b));
       }
     }
-    if (pt == 0) tick_flush(1);
+    __syncwarp();
   } else if (warp == W_ISSUE) {
     // ------------------------------------------------------------------ dA GEMM issuer
     if (lane == 0) {
@@ -567,7 +577,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
       mbar_wait(d2full, gi & 1);
       tick(0);
       tc_fence_after();
-      if (dt == 0) bulk_wait_read0();  // the previous slab has left shared memory (tile 0 is rewritten by this warp)
+      if (lane == 0) bulk_wait_read0();  // the previous slab has left shared memory (tile 0 is rewritten by this warp)
       __syncwarp();
       tick(1);
 #pragma unroll
@@ -604,7 +614,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
       }
       tick(3);
     }
-    if (dt == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
     if (dw == 0) tick_flush(3);
   } else if (warp == W_LOAD) {
     // ------------------------------------------------------------------ input loader
@@ -800,6 +810,26 @@ void chunking(int N, int frames_per_group, int& groups_per_chunk, int& nchunks) 
   nchunks = cdiv(groups, groups_per_chunk);
 }
 
+// backward: one CTA per SM and a ~7k-cycle set-up (both W operands into tensor memory) per CTA: fewer, longer CTAs,
+// their number chosen so that the last wave over the SMs is (nearly) full
+void chunking_bwd(int N, int& groups_per_chunk, int& nchunks) {
+  const int groups = cdiv(N, FB);
+  static const int forced = [] { const char* e = getenv("NEMO_B200_SKIN_BWD_CHUNKS"); return e ? max(1, atoi(e)) : 0; }();
+  int best = 1;
+  if (forced) {
+    best = forced;
+  } else {
+    double best_cost = 1e30;
+    for (int c = 1; c <= 16 && c <= groups; ++c) {
+      const int gpc = cdiv(groups, c), ctas = NT_V * cdiv(groups, gpc);
+      const double cost = (double)cdiv(ctas, num_sms()) * (gpc + 2.0);  // waves x (groups + set-up, in group units)
+      if (cost < best_cost) best_cost = cost, best = c;
+    }
+  }
+  groups_per_chunk = cdiv(groups, best);
+  nchunks = cdiv(groups, groups_per_chunk);
+}
+
 template <int MODE>
 int launch_fwd(const SkinArgs& a, cudaStream_t s) {
   static bool configured = false;
@@ -838,7 +868,7 @@ int launch_bwd_timing(SkinBwdArgs a, cudaStream_t s) {
   const double groups = (double)NT_V * cdiv(a.N, FB);
   static const char* names[5][8] = {
       {"inputs (ring)", "signs", "wait tfull", "tmem ld", "dPO", "wait gfree", "G phase", "-"},
-      {"wait amfree", "Amat store", "bar", "fetch + wait tempty", "T mma issue", "-", "-", "-"},
+      {"wait amfree", "Amat store", "fetch", "-", "-", "-", "-", "-"},
       {"wait gfull0", "wait gfull1", "wait gfull2", "wait gfull3", "mma0", "mma1", "mma2", "mma3"},
       {"wait d2full", "wait slab read", "copy", "sum + bulk reduce", "-", "-", "-", "-"},
       {"-", "-", "-", "-", "-", "-", "-", "-"}};
@@ -892,7 +922,7 @@ extern "C" int nemo_b200_skin_bwd(const float* A, const float* PO, const float* 
   SkinBwdArgs a{};
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.dV = dV; a.signs = signs;
   a.sign_scale = sign_scale; a.dPO = dPO; a.dA = dA; a.N = N;
-  chunking(N, FB, a.groups_per_chunk, a.nchunks);
+  chunking_bwd(N, a.groups_per_chunk, a.nchunks);
   static const int abl = [] { const char* e = getenv("NEMO_B200_SKIN_ABLATE"); return e ? atoi(e) : 0; }();
   a.ablate = abl;
   NB_CUDA(cudaMemsetAsync(dA, 0, sizeof(float) * (size_t)N * 288, s));  // vertex tiles accumulate with reductions
