@@ -195,6 +195,16 @@ def k7_roofline(dev, iters=10):
     return N, out
 
 
+def k7_traffic(n):
+    """dram__bytes_read + dram__bytes_write of the K7 launch pair from the committed ncu --set full capture (None
+    when the capture was taken at another batch size)."""
+    p = os.path.join(ROOT, 'profiles', 'k7_traffic.json')
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d['fwd_dram_bytes'] + d['bwd_dram_bytes'] if d.get('n') == n else None
+
+
 def run_gpu(a):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -285,7 +295,7 @@ def run_gpu(a):
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': 'k_skin_tc_fwd<0> + k_skin_tc_bwd<dV> (K7, vertices written, dV read: 5 streams/frame)',
                      'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': None,
+                     'frac': achieved / peak, 'traffic': k7_traffic(nK7),
                      'algorithmic_bytes_per_launch_pair': alg, 'fwd_ms': tk['fwd'] * 1e3, 'bwd_ms': tk['bwd'] * 1e3,
                      'fwd_frac': 2 * STREAM_BYTES * nK7 / tk['fwd'] / 1e9 / peak,
                      'bwd_frac': 3 * STREAM_BYTES * nK7 / tk['bwd'] / 1e9 / peak},

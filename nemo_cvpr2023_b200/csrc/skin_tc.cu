@@ -91,11 +91,18 @@ struct AmatWriter {
 struct FwdCfg {
   static constexpr int OFF_W = 0;                       // [W hi][W lo]
   static constexpr int OFF_AM = 2 * WT_BYTES;           // 2 buffers x [hi][lo]
-  static constexpr int OFF_RED = OFF_AM + 4 * AM_BYTES;
+  // input ring: the pose offsets of NSTAGE groups (8 slots x 3 components x 512 bytes) are in flight as bulk async
+  // copies issued by a loader warp: the HBM latency is covered by the ring, not by the workers' registers
+  static constexpr int NSTAGE = 2;
+  static constexpr int ST_BYTES = FB * 3 * TILE_V * 4;
+  static constexpr int OFF_ST = OFF_AM + 4 * AM_BYTES;
+  static constexpr int OFF_RED = OFF_ST + NSTAGE * ST_BYTES;
   static constexpr int OFF_BARS = OFF_RED + 256;
-  static constexpr int SMEM_BYTES = OFF_BARS + 64 + 1024;
+  static constexpr int SMEM_BYTES = OFF_BARS + 128 + 1024;
   static constexpr int TMEM_COLS = 256;                 // T: 2 x 128
 };
+static_assert(2 * FwdCfg::SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
+constexpr int FWD_THREADS = 9 * 32;  // 4 workers, 3 Amat writers, T GEMM issuer, loader
 
 struct SkinArgs {
   const float* A;      // (N,24,12)   [MODE 1: mesh a]
@@ -111,7 +118,7 @@ struct SkinArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS, 2) k_skin_tc_fwd(const SkinArgs a) {
   using C_ = FwdCfg;
   constexpr int FG = MODE == 0 ? FB : FB / 2;  // frames per group
   constexpr int NMESH = MODE == 0 ? 1 : 2;
@@ -121,8 +128,12 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
   auto tfull = [&](int b) { return bars + 8u * b; };         // T of buffer b complete          (commit)
   auto tempty = [&](int b) { return bars + 8u * (2 + b); };  // workers done reading T[b]       (128)
   auto amfree = [&](int b) { return bars + 8u * (4 + b); };  // MMAs done reading Amat[b]       (commit)
+  auto amfull = [&](int b) { return bars + 8u * (7 + b); };  // Amat[b] written                 (96)
+  auto sfull = [&](int st) { return bars + 8u * (9 + st); };   // input stage landed            (tx bytes)
+  auto sempty = [&](int st) { return bars + 8u * (11 + st); };  // input stage read by the workers (128)
   const uint32_t tmem_slot = bars + 48;
   const uint32_t sred = sbase + C_::OFF_RED;
+  static_assert(C_::NSTAGE == 2, "barrier slots above");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vt = blockIdx.x % NT_V, chunk = blockIdx.x / NT_V;
@@ -139,12 +150,15 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
       mbar_init(tfull(b), 1);
       mbar_init(tempty(b), 128);
       mbar_init(amfree(b), 1);
+      mbar_init(amfull(b), 96);
+      mbar_init(sfull(b), 1);
+      mbar_init(sempty(b), 128);
     }
     fence_barrier_init();
   }
   if (warp == 7) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   // zero both B-operand buffers once: the k = 24..31 pad columns stay zero for the whole kernel
-  for (int i = tid; i < 4 * AM_BYTES / 16; i += 256)
+  for (int i = tid; i < 4 * AM_BYTES / 16; i += FWD_THREADS)
     sts128(sbase + C_::OFF_AM + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   // W tile -> tf32 hi / lo, K-major (row = vertex, k = joint), pad columns zero
   if (tid < TILE_V) {
@@ -167,42 +181,74 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
   const int last = a.N - 1;
 
   if (warp >= 4) {
-    // ------------------------------------------------------------------ producers (96 threads): Amat + MMA issue
+    // ------------------------------------------------------------------ producers (96 threads): Amat, double buffered;
+    // the transforms of the next group are prefetched into registers while this group's are converted
     if (warp < 7) {
       const int pt = tid - 128;
       AmatWriter aw;
       aw.init(pt);
+      float x[FB][3];
+      auto fetch = [&](int gi) {
+        const int n0 = group_of(gi) * FG;
+#pragma unroll
+        for (int s = 0; s < FB; ++s) {
+          const float* src = (NMESH == 2 && s >= FG) ? a.A2 : a.A;
+          const float* p = src + (size_t)min(n0 + (NMESH == 2 ? (s & (FG - 1)) : s), last) * 288 + pt;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) x[s][i] = __ldg(p + 96 * i);
+        }
+      };
+      fetch(0);
       for (int gi = 0; gi < ng; ++gi) {
         const int b = gi & 1;
         const uint32_t use = gi >> 1;  // how many times buffer b was used before
         if (use > 0) mbar_wait(amfree(b), (use - 1) & 1);
-        const uint32_t am = sbase + C_::OFF_AM + b * 2 * AM_BYTES;
-        const int n0 = group_of(gi) * FG;
-        aw.write(am, pt, [&](int s) {
-          const float* src = (NMESH == 2 && s >= FG) ? a.A2 : a.A;
-          return src + (size_t)min(n0 + (NMESH == 2 ? (s & (FG - 1)) : s), last) * 288;
-        });
+        aw.store(sbase + C_::OFF_AM + b * 2 * AM_BYTES, x);
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 96;" ::: "memory");
-        if (pt == 0) {
-          if (use > 0) mbar_wait(tempty(b), (use - 1) & 1);
-          tc_fence_after();
-          const uint32_t d = tmem_base + b * 128;
-          const uint64_t wh0 = umma_smem_desc(sbase + C_::OFF_W, 16, 1024, LAYOUT_SW128);
-          const uint64_t mh0 = umma_smem_desc(am, 16, 1024, LAYOUT_SW128);
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {  // K = 24 = 3 steps of 8
-            const uint64_t wh = umma_desc_advance(wh0, j * 32), wl = umma_desc_advance(wh0, WT_BYTES + j * 32);
-            const uint64_t mh = umma_desc_advance(mh0, j * 32), ml = umma_desc_advance(mh0, AM_BYTES + j * 32);
-            umma_tf32(d, wl, mh, idesc, j > 0 ? 1u : 0u);
-            umma_tf32(d, wh, ml, idesc, 1u);
-            umma_tf32(d, wh, mh, idesc, 1u);
-          }
-          umma_commit(tfull(b));
-          umma_commit(amfree(b));
+        mbar_arrive(amfull(b));
+        if (gi + 1 < ng) fetch(gi + 1);
+      }
+    } else if (warp == 8) {
+      // ---------------------------------------------------------------- input loader: lane = (slot, component)
+      for (int gi = 0; gi < ng; ++gi) {
+        const int st = gi & 1;
+        const uint32_t use = gi >> 1;
+        if (use > 0) mbar_wait(sempty(st), (use - 1) & 1);
+        if (lane == 0) mbar_arrive_expect_tx(sfull(st), C_::ST_BYTES);
+        __syncwarp();
+        if (lane < FB * 3) {
+          const int s = lane / 3, c = lane % 3;
+          const float* P = (NMESH == 2 && s >= FG) ? a.PO2 : a.PO;
+          const int n = min(group_of(gi) * FG + (NMESH == 2 ? (s & (FG - 1)) : s), last);
+          bulk_g2s(sbase + C_::OFF_ST + st * C_::ST_BYTES + lane * (TILE_V * 4), P + (size_t)n * (3 * VP) + c * VP + v0,
+                   TILE_V * 4, sfull(st));
         }
       }
+    } else if (lane == 0) {
+      // ---------------------------------------------------------------- T GEMM issuer (its own warp: the issue of nine
+      // MMAs blocks for most of their execution time)
+      for (int gi = 0; gi < ng; ++gi) {
+        const int b = gi & 1;
+        const uint32_t use = gi >> 1;
+        mbar_wait(amfull(b), use & 1);
+        if (use > 0) mbar_wait(tempty(b), (use - 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * 128;
+        const uint64_t wh0 = umma_smem_desc(sbase + C_::OFF_W, 16, 1024, LAYOUT_SW128);
+        const uint64_t mh0 = umma_smem_desc(sbase + C_::OFF_AM + b * 2 * AM_BYTES, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {  // K = 24 = 3 steps of 8
+          const uint64_t wh = umma_desc_advance(wh0, j * 32), wl = umma_desc_advance(wh0, WT_BYTES + j * 32);
+          const uint64_t mh = umma_desc_advance(mh0, j * 32), ml = umma_desc_advance(mh0, AM_BYTES + j * 32);
+          umma_tf32(d, wl, mh, idesc, j > 0 ? 1u : 0u);
+          umma_tf32(d, wh, ml, idesc, 1u);
+          umma_tf32(d, wh, mh, idesc, 1u);
+        }
+        umma_commit(tfull(b));
+        umma_commit(amfree(b));
+      }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ workers: one thread per vertex
     const int v = v0 + tid;
@@ -212,23 +258,18 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
     for (int c = 0; c < 3; ++c) bs[c] = __ldg(a.base + c * VP + v);
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     float l1 = 0.f;
-    // pose offsets are prefetched one group ahead into the other register set: HBM reads overlap the arithmetic
-    float pa[FB][3], pb[FB][3];
-    auto load_po = [&](int gi, float (&dst)[FB][3]) {
-      const int n0 = group_of(gi < ng ? gi : ng - 1) * FG;
-#pragma unroll
-      for (int s = 0; s < FB; ++s) {
-        const float* P = (NMESH == 2 && s >= FG) ? a.PO2 : a.PO;
-        const int n = min(n0 + (NMESH == 2 ? (s & (FG - 1)) : s), last);
-        const float* p = P + (size_t)n * (3 * VP) + v;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) dst[s][c] = __ldcs(p + c * VP);
-      }
-    };
-    auto body = [&](int gi, float (&po)[FB][3], float (&pn)[FB][3]) {
+    const uint32_t st_po = sbase + C_::OFF_ST + tid * 4;
+    auto body = [&](int gi) {
       const int b = gi & 1;
       const int n0 = group_of(gi) * FG;
-      load_po(gi + 1, pn);
+      // this group's pose offsets from the ring
+      float po[FB][3];
+      mbar_wait(sfull(b), (gi >> 1) & 1);
+#pragma unroll
+      for (int s = 0; s < FB; ++s)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) po[s][c] = lds32(st_po + b * C_::ST_BYTES + (s * 3 + c) * (TILE_V * 4));
+      mbar_arrive(sempty(b));
       mbar_wait(tfull(b), (gi >> 1) & 1);
       tc_fence_after();
       const uint32_t ta = tmem_base + lane_addr + b * 128;
@@ -281,11 +322,7 @@ __global__ void __launch_bounds__(256, 2) k_skin_tc_fwd(const SkinArgs a) {
         }
       }
     };
-    load_po(0, pa);
-    for (int gi = 0; gi < ng; gi += 2) {
-      body(gi, pa, pb);
-      if (gi + 1 < ng) body(gi + 1, pb, pa);
-    }
+    for (int gi = 0; gi < ng; ++gi) body(gi);
     if (MODE == 1) {
       l1 = warp_sum(l1);
       if (lane == 0) sts32(sred + 4 * warp, l1);
@@ -800,29 +837,20 @@ int num_sms() {
   return n;
 }
 
-// frame groups per CTA: enough CTAs for >= ~8 waves over the SMs (load balance), at least 4 groups per CTA so
-// the W-tile set-up amortises
-void chunking(int N, int frames_per_group, int& groups_per_chunk, int& nchunks) {
+// Frame groups per CTA.  Every CTA pays a set-up (W operands into shared / tensor memory) worth `setup` groups, and
+// the grid runs in waves over 148 x ctas_per_sm slots: pick the chunk count that minimises waves x (groups + set-up).
+void chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int max_chunks, int& groups_per_chunk,
+              int& nchunks) {
   const int groups = cdiv(N, frames_per_group);
-  static const int waves = [] { const char* e = getenv("NEMO_B200_SKIN_WAVES"); return e ? max(1, atoi(e)) : 8; }();
-  int want = max(1, (waves * num_sms()) / NT_V);  // chunks so that 54 * chunks ~ `waves` waves
-  groups_per_chunk = max(min(4, groups), cdiv(groups, want));
-  nchunks = cdiv(groups, groups_per_chunk);
-}
-
-// backward: one CTA per SM and a ~7k-cycle set-up (both W operands into tensor memory) per CTA: fewer, longer CTAs,
-// their number chosen so that the last wave over the SMs is (nearly) full
-void chunking_bwd(int N, int& groups_per_chunk, int& nchunks) {
-  const int groups = cdiv(N, FB);
-  static const int forced = [] { const char* e = getenv("NEMO_B200_SKIN_BWD_CHUNKS"); return e ? max(1, atoi(e)) : 0; }();
+  static const int forced = [] { const char* e = getenv("NEMO_B200_SKIN_CHUNKS"); return e ? max(0, atoi(e)) : 0; }();
   int best = 1;
   if (forced) {
-    best = forced;
+    best = min(forced, groups);
   } else {
     double best_cost = 1e30;
-    for (int c = 1; c <= 16 && c <= groups; ++c) {
+    for (int c = 1; c <= max_chunks && c <= groups; ++c) {
       const int gpc = cdiv(groups, c), ctas = NT_V * cdiv(groups, gpc);
-      const double cost = (double)cdiv(ctas, num_sms()) * (gpc + 2.0);  // waves x (groups + set-up, in group units)
+      const double cost = (double)cdiv(ctas, num_sms() * ctas_per_sm) * (gpc + setup);
       if (cost < best_cost) best_cost = cost, best = c;
     }
   }
@@ -837,7 +865,7 @@ int launch_fwd(const SkinArgs& a, cudaStream_t s) {
     NB_CUDA(cudaFuncSetAttribute(k_skin_tc_fwd<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg::SMEM_BYTES));
     configured = true;
   }
-  k_skin_tc_fwd<MODE><<<NT_V * a.nchunks, 256, FwdCfg::SMEM_BYTES, s>>>(a);
+  k_skin_tc_fwd<MODE><<<NT_V * a.nchunks, FWD_THREADS, FwdCfg::SMEM_BYTES, s>>>(a);
   NB_LAUNCH_CHECK("skin_tc_fwd");
 }
 
@@ -897,7 +925,7 @@ extern "C" int nemo_b200_skin_fwd(const float* A, const float* PO, const float* 
   NB_REQUIRE(A && PO && base && Wt && V && N >= 0, "skin_fwd: bad args");
   SkinArgs a{};
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.V = V; a.N = N;
-  chunking(N, FB, a.groups_per_chunk, a.nchunks);
+  chunking(N, FB, 2, 2.0, 32, a.groups_per_chunk, a.nchunks);
   return launch_fwd<0>(a, S(stream));
 }
 
@@ -909,7 +937,7 @@ extern "C" int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const 
   SkinArgs a{};
   a.A = A_a; a.PO = PO_a; a.A2 = A_b; a.PO2 = PO_b; a.base = base; a.Wt = Wt; a.signs = signs; a.l1_sum = l1_sum;
   a.N = N;
-  chunking(N, FB / 2, a.groups_per_chunk, a.nchunks);
+  chunking(N, FB / 2, 2, 2.0, 32, a.groups_per_chunk, a.nchunks);
   return launch_fwd<1>(a, S(stream));
 }
 
@@ -922,7 +950,7 @@ extern "C" int nemo_b200_skin_bwd(const float* A, const float* PO, const float* 
   SkinBwdArgs a{};
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.dV = dV; a.signs = signs;
   a.sign_scale = sign_scale; a.dPO = dPO; a.dA = dA; a.N = N;
-  chunking_bwd(N, a.groups_per_chunk, a.nchunks);
+  chunking(N, FB, 1, 2.0, 16, a.groups_per_chunk, a.nchunks);
   static const int abl = [] { const char* e = getenv("NEMO_B200_SKIN_ABLATE"); return e ? atoi(e) : 0; }();
   a.ablate = abl;
   NB_CUDA(cudaMemsetAsync(dA, 0, sizeof(float) * (size_t)N * 288, s));  // vertex tiles accumulate with reductions
