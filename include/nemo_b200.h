@@ -125,6 +125,21 @@ int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const float* A_b,
                           const float* base, const float* Wt, uint32_t* signs, float* l1_sum, int N,
                           void* stream);
 
+/* ---------------------------------------------------------------- evaluation metrics
+ * nemo/utils/pose_utils.py:78-159 (compute_similarity_transform[_batch], reconstruction_error), batched: one CTA per
+ * item instead of a numpy loop over frames.  S1, S2 (B,P,3).
+ * point_error:  err[b] = mean_p |S1[b,p] - S2[b,p]|                       (reconstruction_error(pa=False))
+ * procrustes:   S1_hat = s R S1 + t, the similarity transform that takes S1 closest to S2 (proper rotation: the
+ *               reference's SVD solution with its reflection fix); err[b] = mean_p |S1_hat - S2|;
+ *               srt (B,13) = [s, R row-major, t].  S1_hat, err, srt may each be NULL (not all three).
+ * pck2d:        PCK@0.05 of MultiViewModel.eval_2d (nemo/neural_motion_model.py:524-532): pred (B,J,2),
+ *               gt (B,J,3) = x, y, conf, gt_size (B); out2[0] += hits, out2[1] += valid (caller zeroes). */
+int nemo_b200_point_error(const float* S1, const float* S2, int P, int B, float* err, void* stream);
+int nemo_b200_procrustes(const float* S1, const float* S2, int P, int B, float* S1_hat, float* err, float* srt,
+                         void* stream);
+int nemo_b200_pck2d(const float* pred, const float* gt, const float* gt_size, int J, int B, float* out2,
+                    void* stream);
+
 /* ---------------------------------------------------------------- joint read-outs (K7j)
  * smplx VertexJointSelector (picked vertices) and hmr/smpl.py:33-36 (J_regressor_extra . vertices),
  * evaluated WITHOUT the mesh: a read-out is a fixed linear functional of the vertices and skinning is

@@ -2,7 +2,9 @@
 MultiViewModel (:151) and NemoV1..V4 (:3364, :3675, :3786, :3959) with the reference's method names,
 arguments, return values and state_dict keys.  `step`, `warmup`, `opt_cam`, `get_preds_batch`,
 `get_preds` run on the fused engine (fit_engine.FitEngine): hand-written CUDA forward + backward +
-Adam, no autograd graph.  Rendering / offline evaluation methods (:282-2756) are out of scope."""
+Adam, no autograd graph.  `eval_3d` / `eval_2d` (:1056-1282, :522-710) are batched over the frames of a view (the
+reference calls SMPL once per frame) and write the same CSV columns.  Rendering methods are out of scope."""
+import os
 from collections import defaultdict
 from copy import deepcopy
 
@@ -315,6 +317,101 @@ class MultiViewModel(nn.Module):
             for k, v in self.get_preds_batch(vi, fi, add_trans=add_trans).items():
                 all_preds[k].append(v)
         return {k: torch.stack(v) for k, v in all_preds.items()}
+
+    # ---- evaluation: same numbers and CSV columns as the reference, one SMPL call per view
+    def _eval_frames(self, num_frames, num_views, view_idxs):
+        ncol = self.num_frames if num_frames < 0 else min(self.num_frames, num_frames)
+        if len(view_idxs) == 0:
+            view_idxs = np.arange(0, self.num_views if num_views < 0 else min(self.num_views, num_views))
+        frames = [int(np.round(c / ncol * self.num_frames)) for c in range(ncol)]
+        return list(view_idxs), frames
+
+    def _smpl_of_body_pose(self, body_pose):
+        """SMPL(betas=None, body_pose=aa (B,69), global_orient=None, pose2rot=True) as eval_3d calls it (:1144-1151)."""
+        bp = torch.as_tensor(np.asarray(body_pose) if not isinstance(body_pose, torch.Tensor) else body_pose,
+                             dtype=torch.float32).to(self.device).reshape(-1, 69)
+        with torch.no_grad():  # the zero global orientation / betas of the reference call, at the batch size
+            out = self.smpl(betas=None, body_pose=bp, global_orient=torch.zeros(bp.shape[0], 3, device=bp.device),
+                            pose2rot=True)
+        return out.vertices.contiguous(), out.joints[:, :15].contiguous()
+
+    def eval_3d(self, out_dir, num_frames=-1, num_views=-1, view_idxs=[], dynamic_only=False):
+        """:1056-1282.  MPVPE / MPJPE (mm, no Procrustes) of the fitted poses -- and of every baseline pose track the
+        sequences carry (`pose` = VIBE, `vs_pose`, `pare_pose`, `glamr_pose`) -- against `pose_3d_gt`."""
+        import pandas as pd
+        from .utils.pose_utils import reconstruction_error
+        view_idxs, frames = self._eval_frames(num_frames, num_views, view_idxs)
+        pred_dict = self.get_preds()
+        os.makedirs(out_dir, exist_ok=True)
+        stats = defaultdict(list)
+        for view_idx in view_idxs:
+            seq = self.multi_view_seqs.sequences[view_idx]
+            gt_pose = np.asarray(torch.stack(list(seq['pose_3d_gt'])).cpu() if isinstance(seq['pose_3d_gt'], (list, tuple))
+                                 else seq['pose_3d_gt'], dtype=np.float32)
+            fsel = list(frames)
+            if dynamic_only:  # :1082-1116: frames between the first and the last fast GT joint motion
+                _, j_all = self._smpl_of_body_pose(gt_pose[:, 3:])
+                j_all = j_all.cpu().numpy()
+                vel = np.sqrt(((j_all[1:] - j_all[:-1]) ** 2).sum(-1)) * (
+                    30 * self.multi_view_seqs.framerate_multiplier[view_idx])
+                inds = np.where(vel.max(1) >= 2)[0]
+                mask = np.zeros((self.num_frames,))
+                if len(inds):
+                    mask[inds.min():inds.max()] = 1
+                fsel = [f for f in frames if mask[f] != 0]
+            if not fsel:
+                continue
+            v_gt, j_gt = self._smpl_of_body_pose(gt_pose[fsel][:, 3:])
+            tracks = {'ours': pred_dict['poses'][view_idx][fsel]}
+            if 'pose' in seq:
+                tracks['vibe'] = np.asarray(seq['pose'], np.float32)[fsel][:, 3:-1]
+            for name, key, sl in (('vs', 'vs_pose', slice(3, -1)), ('pare', 'pare_pose', slice(3, -1)),
+                                  ('glamr', 'glamr_pose', slice(None, -1))):
+                if key in seq:
+                    tracks[name] = np.asarray(seq[key], np.float32)[fsel][:, sl]
+            for name, bp in tracks.items():
+                v, j = self._smpl_of_body_pose(bp)
+                stats['mpjpe-' + name].append(1000 * reconstruction_error(j_gt, j, pa=False))
+                stats['mpvpe-' + name].append(1000 * reconstruction_error(v_gt, v, pa=False))
+            print(f"View: {view_idx}, MPVPE: {stats['mpvpe-ours'][-1]:.2f}, MPJPE: {stats['mpjpe-ours'][-1]:.2f}")
+        df = pd.DataFrame(stats)
+        df.to_csv(os.path.join(out_dir, 'eval_3d.csv' if not dynamic_only else 'eval_3d_dynamic.csv'))
+        return df
+
+    def eval_2d(self, out_dir, num_frames=-1, num_views=-1, view_idxs=[]):
+        """:522-710.  ReconError2D (`rmse` keypoint loss) and PCK@0.05 of the re-projected fitted joints -- and of every
+        2-D baseline track the sequences carry -- against the `gt` 2-D labels (first 15 joints)."""
+        import pandas as pd
+        view_idxs, frames = self._eval_frames(num_frames, num_views, view_idxs)
+        gt_all, bbox = self.collate_gt_2d(label_type='gt')
+        base = {'op': self.collate_gt_2d(label_type='op')[0]}
+        seq0 = self.multi_view_seqs.sequences[0]
+        for name, key, on in (('vibe', 'vibe_joints2d', True), ('vs', 'vs_joints2d', self.args.include_vs),
+                              ('pare', 'pare_joints2d', self.args.include_pare)):
+            if on and key in seq0:
+                base[name] = self.collate_gt_2d(label_type=name)[0]
+        pred = self.get_preds()
+        V, F = pred['j'].shape[:2]
+        with torch.no_grad():
+            p2d = self.learned_camera_projection(pred['j'].reshape(-1, 25, 3), pred['view_idx'].reshape(-1))
+        base = dict(ours=p2d.reshape(V, F, 25, 2), **base)
+        os.makedirs(out_dir, exist_ok=True)
+        stats = defaultdict(list)
+        fi = torch.as_tensor(frames, device=gt_all.device)
+        for view_idx in view_idxs:
+            gt = gt_all[view_idx][fi][:, :15].contiguous()
+            size = bbox[view_idx][fi].contiguous()
+            for name, pts in base.items():
+                p = pts[view_idx][fi][:, :15, :2].float().contiguous()
+                r = self.keypoint_loss(p, gt[..., :2], gt[..., 2:], loss_type='rmse').mean().item()
+                hits = torch.zeros(2, device=p.device)
+                Fn.lib.pck2d(p, gt, size, 15, p.shape[0], hits)
+                stats['recon_error_2d-' + name].append(r)
+                stats['pck-' + name].append(float(100 * hits[0] / hits[1]))
+            print(f"View: {view_idx}, ReconError2D: {stats['recon_error_2d-ours'][-1]:.2f}, PCK: {stats['pck-ours'][-1]:.1f}")
+        df = pd.DataFrame(stats)
+        df.to_csv(os.path.join(out_dir, 'eval_2d.csv'))
+        return df
 
     def _get_smpl_given_poses(self, pose_input, orient, pose_type):
         """:2963-2976"""

@@ -225,3 +225,20 @@ def test_step_matches_reference(version, sm, vp, gmm):
             if k.startswith(pre):
                 # Adam's first steps move each weight by ~lr regardless of gradient scale
                 assert_abs(npy(m.p[k[len(pre):]]), ref, 2e-5 * max(1.0, np.abs(ref).max()), k)
+
+
+def test_metrics_oracle():
+    """oracle/pose_metrics.py == the reference's pose_utils / f_pck outputs (tests/golden/metrics.npz)."""
+    from oracle import pose_metrics as M
+    g = gold('metrics')
+    for name in ('j', 'v', 'refl'):
+        S1, S2 = g[name + '_S1'].astype(np.float64), g[name + '_S2'].astype(np.float64)
+        hat = np.stack([M.compute_similarity_transform(a, b)[0] for a, b in zip(S1, S2)])
+        assert np.abs(hat - g[name + '_hat']).max() < 1e-6
+        if name != 'refl':
+            assert np.allclose(M.reconstruction_error(S1, S2, pa=True, reduction=None), g[name + '_err_pa'], rtol=1e-9)
+            assert np.allclose(M.reconstruction_error(S1, S2, pa=False, reduction=None), g[name + '_err'], rtol=1e-12)
+            _, s, R, t = M.compute_similarity_transform(S1[0], S2[0])
+            assert np.allclose(np.concatenate([[s], R.reshape(-1), t]), g[name + '_srt0'], atol=1e-9)
+    assert abs(M.pck(g['pck_pred'].astype(np.float64), g['pck_gt'].astype(np.float64), g['pck_size'].astype(np.float64))
+               - float(g['pck'])) < 1e-4
