@@ -518,7 +518,7 @@ class MultiViewModel(nn.Module):
             w, _ = e.forward_backward(vi, fi, update=True, mode='warmup')
             self.opt_motion.step()
             self.opt_phase.step()
-            losses.append(w['acc'][2])
+            losses.append(w['acc'][2].clone())   # `acc` is a reused workspace slot
         return [float(x) for x in torch.stack(losses).cpu()]
 
     def opt_cam(self, cam_opt_steps=2000):
