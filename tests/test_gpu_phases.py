@@ -109,3 +109,47 @@ def test_save_load_roundtrip(tmp_path):
     pa, pb = m.engine.named_params(), m2.engine.named_params()
     for k in pa:
         assert torch.allclose(pa[k], pb[k], rtol=1e-4, atol=1e-6), k
+
+
+def test_v4_opt_cam_iteration_matches_oracle():
+    """NemoV4.opt_cam (:4060-4149): per-view-mean 2D loss with the articulated pose detached + weighted 3D pose loss;
+    every optimiser steps.  One iteration on a fixed batch: all gradients."""
+    from nemo_cvpr2023_b200.nemo import neural_motion_model as nmm
+    from nemo_cvpr2023_b200.nemo.multi_view_sequence import SyntheticMultiViewSequence
+    V, Fr = 4, 12
+    args = assets.default_args(h_dim=48, phase_rbf_dim=12, instance_code_size=4, monotonic_network_n_nodes=16,
+                               batch_size=40, weight_3d_loss=7.0)
+    params = assets.make_fit_params(args, V, seed=31)
+    data = assets.make_fit_data(V, Fr, seed=32)
+    r = np.random.RandomState(33)
+    data['points2d_gt_all'][..., 0] = 540 + 150 * r.standard_normal((V, Fr, 25))
+    data['points2d_gt_all'][..., 1] = 960 + 150 * r.standard_normal((V, Fr, 25))
+    orc = O.FitOracle(args, O.to_torch(params), O.to_torch(assets.make_smpl_assets(0)),
+                      O.to_torch(assets.make_vposer_weights(2)), O.to_torch(assets.make_gmm(3)), O.to_torch(data),
+                      version=4).build_optimizers()
+    m = nmm.NemoV4(args, SyntheticMultiViewSequence(data=data), DEV, init_params=params)
+    vi, fi = torch.tensor(r.randint(0, V, 40)), torch.tensor(r.randint(0, Fr, 40))
+    pred = orc.get_preds_batch(vi, fi, detach_pose=True)
+    p2d = O.learned_camera_projection(pred['j'], vi, orc.p['learned_cameras'], orc.focal, orc.data['IMG_D0'],
+                                      orc.data['IMG_D1'])
+    gt = orc.data['points2d_gt_all'][vi, fi]
+    loss_all = O.keypoint_loss(p2d, gt[..., :2], gt[..., 2:], orc.data['gt_bbox_size'][vi, fi], args.loss)
+    loss = O.per_view_mean(loss_all, gt[..., 2:], vi)
+    l3 = O.keypoint_loss(pred['poses'], orc.data['hmr_theta'][vi, fi], orc.data['hmr_mask'][vi, fi],
+                         loss_type='mse_robust').mean()
+    (loss + args.weight_3d_loss * l3).backward()
+    m.engine.forward_backward(vi.to(DEV), fi.to(DEV), update=True, mode='opt_cam', detach_pose=True)
+    grads = m.engine.named_grads()
+    n = 0
+    for k, p in orc.p.items():
+        if p.grad is None or k == 'learned_betas':
+            continue
+        if float(p.grad.abs().max()) == 0.0:
+            assert float(grads[k].abs().max()) == 0.0, k
+            continue
+        assert_grad(npy(grads[k]), npy(p.grad), what='V4 opt_cam ' + k)
+        n += 1
+    assert n >= 10
+    torch.manual_seed(1)
+    m.opt_cam(3)   # the loop itself: samples, detaches, steps every optimiser
+    assert all(torch.isfinite(p).all() for p in m.engine.named_params().values())
