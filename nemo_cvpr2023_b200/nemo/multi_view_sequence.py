@@ -31,3 +31,139 @@ class SyntheticMultiViewSequence:
 
 
 MultiViewSequence = SyntheticMultiViewSequence
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Custom-video adaptor: `DemoMultiViewSequence` of nemo/multi_view_sequence.py:92-247, the
+# loader behind custom_video/nemo-run.sh.  Same directory convention (`<exp_dir>/<name>.frames/*.png`,
+# `<name>.op/%06d_keypoints.json` = OpenPose BODY_25, `<name>.vibe/vibe_output.pkl`, optional `<name>.cam.pickle`),
+# same frame sampling (`tidx = floor(phase * n_seq_frames)`), same person selection, same output layout
+# (`sequences[v][key][f]`).  Host-side file IO only; nothing here touches the GPU.
+def prepare_person_dict(person_output, max_frames):
+    """:30-48: scatter a VIBE track onto all `max_frames` frames (zeros where the person is absent) + `mask`."""
+    new_output = {}
+    for key in person_output:
+        if key in ['betas', 'frame_ids']:
+            new_output[key] = person_output[key]
+            continue
+        old_values = person_output[key]
+        if old_values is None:
+            continue
+        shape = list(old_values.shape)
+        shape[0] = max_frames
+        new_values = np.zeros(shape).astype('float32')
+        new_values[person_output['frame_ids']] = old_values
+        new_output[key] = new_values
+    mask = np.zeros((max_frames)).astype('float32')
+    mask[person_output['frame_ids']] = 1
+    new_output['mask'] = mask
+    return new_output
+
+
+def prepare_vibe_dict(vibe_output, max_frames):
+    """:51-55"""
+    return {pid: prepare_person_dict(vibe_output[pid], max_frames) for pid in vibe_output}
+
+
+def select_person_at_center(vibe_output, img_size, max_frames, all_gt_2d):
+    """:58-89: the track whose mean 2-D joint centre is closest (masked mean distance) to the labels' centre."""
+    if vibe_output == {}:
+        return None
+    ret_key, best_dist = 0, np.inf
+    for key in vibe_output:
+        person_output = vibe_output[key]
+        joints2d = person_output['joints2d_img_coord' if 'joints2d_img_coord' in person_output else 'smpl_joints2d']
+        centers = joints2d[:, :15].mean(1)
+        gt_centers = all_gt_2d.mean(1)
+        mask = person_output['mask']
+        cur_dist = (np.sqrt(((np.array(centers) - np.array(gt_centers)) ** 2).sum(-1)) * mask).sum() / mask.sum()
+        if cur_dist < best_dist:
+            ret_key, best_dist = key, cur_dist
+    return vibe_output[ret_key]
+
+
+def _read_openpose(op_file, scale2=False):
+    """one BODY_25 person -> (25,3) [x, y, conf]; nobody -> zeros; several people -> ValueError (:147-158, :185-197)"""
+    import json
+    people = json.load(open(op_file, 'r'))['people']
+    if len(people) == 1:
+        pose = np.array(people[0]['pose_keypoints_2d']).reshape(25, 3)
+        if scale2:
+            pose[:, :2] *= 2
+        return pose
+    if len(people) == 0:
+        return np.zeros((25, 3))
+    raise ValueError('multiple people in %s' % op_file)
+
+
+class DemoMultiViewSequence:
+    def __init__(self, nemo_data_cfg, start_phase, num_frames):
+        import os
+        import os.path as osp
+        from collections import defaultdict
+
+        import joblib
+        self.nemo_data_cfg, self.start_phase = nemo_data_cfg, start_phase
+        self.sequences = []
+        exp_dir, names = nemo_data_cfg['exp_dir'], nemo_data_cfg['videos']['names']
+
+        def n_png(name):
+            return len([s for s in os.listdir(osp.join(exp_dir, name + '.frames')) if s.endswith('.png')])
+
+        min_num_frames = min(n_png(name) for name in names)
+        start_min_frame = np.round(min_num_frames * start_phase)
+        self.num_frames = int(min([num_frames, min_num_frames - start_min_frame - 1]))
+        max_sizes = [0, 0]
+        self.video_img_dir_list, self.n_seq_frames_list, self.gt_camera_dicts, self.framerate_multiplier = [], [], [], []
+        for view_idx, name in enumerate(names):
+            cur_seq = defaultdict(list)
+            img_dir, op_out_dir = osp.join(exp_dir, name + '.frames'), osp.join(exp_dir, name + '.op')
+            cam_path = osp.join(exp_dir, name + '.cam.pickle')
+            if osp.exists(cam_path):
+                self.gt_camera_dicts.append(joblib.load(cam_path))
+            n_seq_frames = n_png(name)
+            assert start_phase == 0
+            self.framerate_multiplier.append(n_seq_frames / self.num_frames)
+            self.video_img_dir_list.append(img_dir)
+            self.n_seq_frames_list.append(n_seq_frames)
+            dummy_img = self.get_raw_image(view_idx, 0)
+            # the reference doubles the coordinates here unconditionally (:151) -- only used to pick the VIBE track
+            all_op_2d = np.array([_read_openpose(osp.join(op_out_dir, f"{t + 1:06d}_keypoints.json"), True)[:15, :2]
+                                  for t in range(n_seq_frames)])
+            hmr_output = prepare_vibe_dict(joblib.load(osp.join(exp_dir, name + '.vibe', 'vibe_output.pkl')), n_seq_frames)
+            person = select_person_at_center(hmr_output, dummy_img.shape[:2], n_seq_frames, all_op_2d)
+            hmr_pose = np.concatenate([person['pose'], np.ones((n_seq_frames, 1))], 1)
+            for frame_idx in range(self.num_frames):
+                phase = start_phase + (1 - start_phase) * float(frame_idx / self.num_frames)
+                tidx = int(np.floor(phase * n_seq_frames))
+                cur_seq['pose_2d_op'].append(_read_openpose(osp.join(op_out_dir, f"{tidx + 1:06d}_keypoints.json"),
+                                                            'opencap' in exp_dir))
+                cur_seq['pose'].append(hmr_pose[tidx])
+                cur_seq['vibe_cam'].append(person['orig_cam'][tidx])
+                cur_seq['vibe_verts'].append(person['verts'][tidx])
+                cur_seq['vibe_mask'].append(person['mask'][tidx])
+                cur_seq['vibe_joints2d'].append(person['joints2d_img_coord'][tidx])
+            self.sequences.append(cur_seq)
+            for i in range(2):
+                max_sizes[i] = max(max_sizes[i], dummy_img.shape[i])
+        self.IMG_D0, self.IMG_D1 = max_sizes
+        self.num_views = len(self.sequences)
+
+    def get_raw_image(self, view_idx, frame_idx):
+        """:224-240"""
+        import os
+
+        import cv2
+        phase = self.start_phase + (1 - self.start_phase) * float(frame_idx / self.num_frames)
+        tidx = int(np.floor(phase * self.n_seq_frames_list[view_idx]))
+        path = os.path.join(self.video_img_dir_list[view_idx], f"{tidx + 1:06d}.png")
+        if not os.path.exists(path):
+            raise ValueError(path, ' doesnt exist.')
+        return cv2.imread(path)[..., ::-1]
+
+    def get_image(self, view_idx, frame_idx):
+        """:242-247"""
+        raw = self.get_raw_image(view_idx, frame_idx)
+        im = np.zeros((self.IMG_D0, self.IMG_D1, 3))
+        im[:raw.shape[0], :raw.shape[1]] = raw
+        return im.astype('uint8')

@@ -68,3 +68,39 @@ def assert_adam_param(p, ref, what='', lr=1e-1):
     frac = (d > 2e-5 * scale).mean()
     assert frac <= 5e-3, '%s: %.3f%% of entries differ by more than 2e-5' % (what, 100 * frac)
     assert d.max() <= 2.5 * lr, '%s: max abs err %.3e' % (what, d.max())
+
+
+def make_demo_tree(root, seed=11):
+    """A seeded stand-in for a custom-video experiment directory in the layout `DemoMultiViewSequence` reads
+    (nemo/multi_view_sequence.py:92-222): two videos with different frame counts and image sizes, OpenPose BODY_25
+    JSONs (one frame without a detection), a VIBE pickle with two tracked people (one present on a subset of frames).
+    Returns the `nemo_data_cfg` dict."""
+    import json
+
+    import cv2
+    import joblib
+    r = np.random.RandomState(seed)
+    names = ['swing.0', 'swing.1']
+    for vi, (name, T, hw) in enumerate(zip(names, (14, 11), ((48, 64), (40, 72)))):
+        fr, op, vb = (os.path.join(root, name + s) for s in ('.frames', '.op', '.vibe'))
+        for d in (fr, op, vb):
+            os.makedirs(d, exist_ok=True)
+        centre = r.uniform(10, 30, (T, 1, 2))
+        for t in range(T):
+            cv2.imwrite(os.path.join(fr, f"{t + 1:06d}.png"), r.randint(0, 255, hw + (3,)).astype(np.uint8))
+            kp = np.concatenate([centre[t] + r.standard_normal((25, 2)), r.uniform(0, 1, (25, 1))], 1)
+            people = [] if (vi == 0 and t == 3) else [{'pose_keypoints_2d': kp.reshape(-1).tolist()}]
+            json.dump({'people': people}, open(os.path.join(op, f"{t + 1:06d}_keypoints.json"), 'w'))
+
+        def person(ids, offset):
+            n = len(ids)
+            return {'frame_ids': np.asarray(ids), 'betas': r.standard_normal((n, 10)).astype(np.float32),
+                    'pose': r.standard_normal((n, 72)).astype(np.float32),
+                    'orig_cam': r.standard_normal((n, 4)).astype(np.float32),
+                    'verts': r.standard_normal((n, 20, 3)).astype(np.float32),
+                    'joints2d_img_coord': (2 * centre[ids] + offset + r.standard_normal((n, 49, 2))).astype(np.float32),
+                    'joints3d': None}
+        joblib.dump({1: person(list(range(2, T - 1)), 40.0), 2: person(list(range(T)), 1.0)},
+                    os.path.join(vb, 'vibe_output.pkl'))
+    joblib.dump({'R': np.eye(3)}, os.path.join(root, names[0] + '.cam.pickle'))
+    return {'exp_dir': root, 'videos': {'names': names}}
