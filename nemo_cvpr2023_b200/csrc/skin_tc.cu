@@ -357,8 +357,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) k_skin_tc_fwd(const SkinArgs a
 // quarters 0 / 1: the W_lo half goes through a shared staging tile, the W_hi warp adds it and reduces into global
 // dA (N,24,12) with 16-byte vector reductions -- the 54 vertex tiles add up); 1 loader feeding the input ring.
 struct BwdCfg {
-  static constexpr int GT_LO = NROW * 128;               // rows 96..191 of a k block: the lo part
-  static constexpr int GT_KB_BYTES = 2 * NROW * 128;     // one 32-vertex k block of G: [hi | lo] = 192 rows x 128 B
+  // G: MN-major B operand, n = [hi (f,r,c) 0..95 | lo 96..191] in six 32-wide blocks, k = vertex:
+  // [n block q][k row = 128 bytes of 32 n], 32-byte chunk j of a row stored at chunk (j ^ (k & 3))
+  static constexpr int GQ_BYTES = TILE_V * 128;          // one n block: 128 k rows
+  static constexpr int GT_LO = 3 * GQ_BYTES;             // n blocks 3..5: the lo part
   static constexpr int OFF_AM = 0;                       // 2 buffers x [hi][lo] x 12 KB
   static constexpr int OFF_G = OFF_AM + 4 * AM_BYTES;    // 4 k blocks x 24 KB
   // input ring: the pose offsets (planar: 3 x 512 bytes per frame) and the upstream vertex gradient (interleaved xyz:
@@ -370,17 +372,15 @@ struct BwdCfg {
   static constexpr int DV_SLOT = TILE_V * 12 + 16;
   static constexpr int ST_DV_BYTES = FB * DV_SLOT;
   static constexpr int ST_BYTES = ST_PO_BYTES + ST_DV_BYTES;
-  static constexpr int OFF_ST = OFF_G + 4 * GT_KB_BYTES;
-  // accumulator staging: three partial sums (. G_hi and . G_lo of the W_hi lanes, . G_hi of the W_lo lanes), each laid
-  // out exactly like the group's slab of global dA: [frame][joint][12] (a lane = joint writes 16-byte pieces with a
-  // 48-byte stride: conflict free)
+  static constexpr int OFF_ST = OFF_G + 6 * GQ_BYTES;
+  // accumulator staging: the group's slab of global dA, [frame][joint][12], double buffered
   static constexpr int STG_BYTES = FB * 288 * 4;
   static constexpr int OFF_STG = OFF_ST + NSTAGE * ST_BYTES;
-  static constexpr int OFF_BARS = OFF_STG + 3 * STG_BYTES;
+  static constexpr int OFF_BARS = OFF_STG + 2 * STG_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
   static constexpr int TM_T = 0;        // T: 96 columns
   static constexpr int TM_WT = 96;      // [W_hi^T ; W_lo^T]: 128 columns (k = vertex)
-  static constexpr int TM_D = 224;      // dA: 192 columns [. G_hi | . G_lo]
+  static constexpr int TM_D = 224;      // dA: 192 columns [. G_hi | . G_lo], TWO M = 64 accumulators (lane offsets 0 / 16)
   static constexpr int TM_W = 416;      // W tile: 32 hi + 32 lo columns
   static constexpr int TMEM_COLS = 512;
 };
@@ -398,7 +398,7 @@ struct SkinBwdArgs {
 };
 
 constexpr int NWORK = 16;                 // worker warps: warp = 4 * (frame pair of the group) + (TMEM lane quarter)
-constexpr int BWD_THREADS = (NWORK + 9) * 32;
+constexpr int BWD_THREADS = (NWORK + 14) * 32;
 
 template <bool HAS_DV, bool HAS_SIGNS, bool TIMING = false>
 __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArgs a) {
@@ -422,8 +422,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   const uint32_t tfull = bars, tempty = bars + 8;               // T complete (commit) / read by the workers (512)
   auto amfree = [&](int b) { return bars + 8u * (2 + b); };     // T GEMM done reading Amat[b]       (commit)
   auto amfull = [&](int b) { return bars + 8u * (26 + b); };    // Amat[b] written                   (96)
-  const uint32_t d2full = bars + 8u * 4;                        // dA complete                       (commit)
-  const uint32_t d2empty = bars + 8u * 6;                       // dA copied to the staging tiles    (96)
+  auto d2full = [&](int b) { return bars + 8u * (4 + b); };     // dA[b] complete                    (commit)
+  auto d2empty = [&](int b) { return bars + 8u * (6 + b); };    // dA[b] copied to the staging tiles (128)
   auto gfull = [&](int kb) { return bars + 8u * (8 + kb); };    // G k block written                 (128)
   auto gfree = [&](int kb) { return bars + 8u * (12 + kb); };   // dA GEMM done reading the k block  (commit)
   auto sfull = [&](int st) { return bars + 8u * (16 + st); };   // input stage landed        (tx bytes [+ 32 cp.async])
@@ -449,8 +449,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
       mbar_init(amfree(b), 1);
       mbar_init(amfull(b), 96);
     }
-    mbar_init(d2full, 1);
-    mbar_init(d2empty, 96);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(d2full(b), 1);
+      mbar_init(d2empty(b), 256);
+    }
     for (int kb = 0; kb < 4; ++kb) {
       mbar_init(gfull(kb), NWORK * 8);
       mbar_init(gfree(kb), 1);
@@ -461,10 +463,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
     }
     fence_barrier_init();
   }
-  // warps [W_PROD, W_PROD+3): Amat writers; W_ISSUE: dA GEMM; W_DRAIN, W_DRAIN+1, W_DRAIN+4: accumulator drain
-  // (TMEM lane quarters 0, 1, 0); W_LOAD: input ring; W_TISSUE: T GEMM
-  constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3, W_DRAIN = NWORK + 4, W_LOAD = NWORK + 6, W_TISSUE = NWORK + 7;
-  static_assert(W_DRAIN % 4 == 0, "drain warps W_DRAIN, W_DRAIN+4 read TMEM lane quarter 0, W_DRAIN+1 quarter 1");
+  // warps [W_PROD, W_PROD+3): Amat writers; W_ISSUE: dA GEMM; [W_DRAIN, W_DRAIN+4): accumulator drain, one warp per
+  // TMEM lane quarter; W_LOAD: input ring; W_TISSUE: T GEMM
+  constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3, W_DRAIN = NWORK + 4, W_LOAD = NWORK + 12, W_TISSUE = NWORK + 13;
+  static_assert(W_DRAIN % 4 == 0, "drain warp W_DRAIN + q reads TMEM lane quarter q");
   if (warp == W_ISSUE) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   // zero Amat: its pad columns k = 24..31 stay zero for the whole kernel (G is fully rewritten every group)
   for (int i = tid; i < 4 * AM_BYTES / 16; i += THREADS)
@@ -489,8 +491,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
       tmem_st32(trow + C_::TM_W, h);
       tmem_st32(trow + C_::TM_W + 32, l);
     }
-    // A operand of the dA GEMM: lane = joint (warp 0: hi part, warp 1: lo part, warps 2-3: zero), column = vertex
-    const float* wrow = a.Wt + (size_t)min(lane, NJ - 1) * VP + v0;
+    // A operand of the dA GEMM, M = 64, column = vertex.  An M = 64 operand / accumulator keeps row r in lane
+    // 32 (r / 16) + r % 16 (+ 16 for a second copy: measured, tools/ubench/mma_m64*.cu; operand and accumulator must
+    // use the same lane offset), so the operand is stored twice and the two accumulators of the double-buffered dA
+    // GEMM share their 192 columns.  Rows of TMEM lane quarter q: [W_hi^T joints 6q..6q+5 | W_lo^T joints 6q..6q+5 |
+    // 4 zero] -- the hi and lo parts of a joint sit six lanes apart in ONE quarter, so the drain warp of the quarter
+    // adds them with a shuffle.
+    const int wrow_l = lane & 15;                              // row within the quarter (both copies)
+    const int wrow_j = 6 * warp + (wrow_l < 6 ? wrow_l : wrow_l - 6);
+    const bool wrow_on = wrow_l < 12, wrow_hi = wrow_l < 6;
+    const float* wrow = a.Wt + (size_t)min(wrow_j, NJ - 1) * VP + v0;
 #pragma unroll 1
     for (int c4 = 0; c4 < 4; ++c4) {
       uint32_t x[32];
@@ -502,7 +512,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
         for (int e = 0; e < 4; ++e) {
           float hi, lo;
           tf32_split(ws[e], hi, lo);
-          x[4 * i + e] = (warp < 2 && lane < NJ) ? __float_as_uint(warp == 0 ? hi : lo) : 0u;
+          x[4 * i + e] = wrow_on ? __float_as_uint(wrow_hi ? hi : lo) : 0u;
         }
       }
       tmem_st32(trow + C_::TM_WT + c4 * 32, x);
@@ -514,7 +524,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   __syncthreads();
   tc_fence_after();
   constexpr uint32_t idesc = umma_idesc_tf32(128, NROW, 0, 0);
-  constexpr uint32_t idesc_d = umma_idesc_tf32(128, 2 * NROW, 0, 0);
+  constexpr uint32_t idesc_d = umma_idesc_tf32(64, 2 * NROW, 0, 1);  // B = G, MN-major
 
   if (warp >= W_PROD && warp < W_ISSUE) {
     // ------------------------------------------------------------------ Amat writers (double buffered)
@@ -572,87 +582,95 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   } else if (warp == W_ISSUE) {
     // ------------------------------------------------------------------ dA GEMM issuer
     if (lane == 0) {
-      const uint64_t gh0 = umma_smem_desc(sbase + C_::OFF_G, 16, 1024, LAYOUT_SW128);
+      // LBO = stride between n blocks, SBO = 512 (4 k rows); a k step of 8 vertices = 1024 bytes
+      const uint64_t gh0 = umma_smem_desc(sbase + C_::OFF_G, C_::GQ_BYTES, 512, LAYOUT_SW128_BASE32B);
       const uint32_t wt = tmem_base + C_::TM_WT;
       tprev = (uint32_t)clock();
       // one MMA per k step: N = 192 = [G_hi | G_lo] (a tf32 MMA costs ~96 cycles whatever its N up to ~176 and
       // ~106 at N = 192 -- measured, tools/ubench/mma_pace.cu -- so the kernel is paced by its MMA COUNT)
-      const uint32_t d = tmem_base + C_::TM_D;
       for (int gi = 0; gi < ng; ++gi) {
+        const int b = gi & 1;
+        const uint32_t use = gi >> 1;
+        const uint32_t boff = (uint32_t)(16 * b) << 16;  // accumulator AND operand copy of buffer b
+        const uint32_t d = tmem_base + C_::TM_D + boff;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           tick(4 + kb);
           mbar_wait(gfull(kb), gi & 1);
           tick(kb);
-          if (kb == 0 && gi > 0) mbar_wait(d2empty, (gi - 1) & 1);
+          if (kb == 0 && use > 0) mbar_wait(d2empty(b), (use - 1) & 1);
           tc_fence_after();
           if (!(a.ablate & 4))
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_tf32_ts(d, wt + kb * 32 + ks * 8, umma_desc_advance(gh0, kb * C_::GT_KB_BYTES + ks * 32), idesc_d,
+            umma_tf32_ts(d, wt + boff + kb * 32 + ks * 8, umma_desc_advance(gh0, (kb * 32 + ks * 8) * 128), idesc_d,
                          (kb | ks) ? 1u : 0u);
           umma_commit(gfree(kb));
         }
-        umma_commit(d2full);
+        umma_commit(d2full(b));
       }
       tick_flush(2);
     }
     __syncwarp();
-  } else if (warp == W_DRAIN || warp == W_DRAIN + 1 || warp == W_DRAIN + 4) {
-    // ------------------------------------------------------------------ accumulator drain
-    // The accumulator is single buffered (tensor memory is full), so it is released as soon as it has been COPIED:
-    // three warps move 96 columns each into the staging tiles, then add the three partial sums in place and ONE
-    // thread hands the group's 9 KB slab to the bulk-reduce engine (cp.reduce.async.bulk .add.f32 into global dA):
-    // no per-thread atomics, the LSU never sees the 54-way accumulation over vertex tiles.
-    const int dw = warp == W_DRAIN ? 0 : (warp == W_DRAIN + 4 ? 1 : 2);  // staging tile
-    const int dt = dw * 32 + lane;
-    const uint32_t ta = tmem_base + ((uint32_t)(dw == 2 ? 32 : 0) << 16) + C_::TM_D + (dw == 1 ? NROW : 0);
-    const uint32_t stg0 = sbase + C_::OFF_STG;
-    const uint32_t stg = stg0 + dw * C_::STG_BYTES + lane * 48;
+  } else if (warp >= W_DRAIN && warp < W_DRAIN + 8) {
+    // ------------------------------------------------------------------ accumulator drain: one warp per lane quarter
+    // Buffer b of the accumulator lives in lanes [16b, 16b + 16) of every quarter; quarter q carries joints 6q..6q+5:
+    // lanes +0..5 = W_hi^T rows (columns [. G_hi | . G_lo]), lanes +6..11 = W_lo^T rows (only . G_hi counts).
+    // dA[j][f][.] = hi[. G_hi] + hi[. G_lo] + lo[. G_hi]: two column runs of the own lane plus one shuffle from six
+    // lanes up, all in registers; the sums go straight into the group's slab (laid out like global dA) and ONE thread
+    // hands the 9 KB slab to the bulk-reduce engine (cp.reduce.async.bulk .add.f32): no per-thread atomics, the LSU
+    // never sees the 54-way accumulation over vertex tiles.  With two accumulators and two slabs all of this overlaps
+    // the next group's MMAs.
+    // two warps per quarter: frame pairs {0, 1} and {2, 3}
+    const int q = (warp - W_DRAIN) & 3, fh = (warp - W_DRAIN) >> 2, dt = (warp - W_DRAIN) * 32 + lane;
+    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + C_::TM_D;
     tprev = (uint32_t)clock();
     for (int gi = 0; gi < ng; ++gi) {
-      mbar_wait(d2full, gi & 1);
+      const int b = gi & 1;
+      mbar_wait(d2full(b), (gi >> 1) & 1);
       tick(0);
       tc_fence_after();
-      if (lane == 0) bulk_wait_read0();  // the previous slab has left shared memory (tile 0 is rewritten by this warp)
-      __syncwarp();
+      const uint32_t slab = sbase + C_::OFF_STG + b * C_::STG_BYTES;
+      if (gi >= 2) {  // the bulk reduction that read this slab two groups ago has left shared memory
+        if (dt == 0) bulk_wait_read1();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
       tick(1);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {  // four frames = 48 accumulator columns per batch of loads
-        uint32_t t[48];
-        tmem_ld16(ta + h * 48, t);
-        tmem_ld16(ta + h * 48 + 16, t + 16);
-        tmem_ld16(ta + h * 48 + 32, t + 32);
+      const int jl = lane - 16 * b;          // 0..5: W_hi row of joint 6q + jl
+      const bool on = jl >= 0 && jl < 6;
+      const uint32_t srow = slab + (6 * q + jl) * 48;
+#pragma unroll 1
+      for (int fp = 2 * fh; fp < 2 * fh + 2; ++fp) {  // two frames = 24 columns of each half per batch
+        uint32_t t[24], u[24];
+        tmem_ld16(ta + fp * 24, t);
+        tmem_ld8(ta + fp * 24 + 16, t + 16);
+        tmem_ld16(ta + NROW + fp * 24, u);
+        tmem_ld8(ta + NROW + fp * 24 + 16, u + 16);
         tmem_ld_wait();
-        if (lane < NJ) {
+        float v[24];
 #pragma unroll
-          for (int q = 0; q < 12; ++q)
-            sts128(stg + (h * 4 + q / 3) * 1152 + (q % 3) * 16,
-                   make_float4(__uint_as_float(t[4 * q]), __uint_as_float(t[4 * q + 1]), __uint_as_float(t[4 * q + 2]),
-                               __uint_as_float(t[4 * q + 3])));
+        for (int i = 0; i < 24; ++i)
+          v[i] = __uint_as_float(t[i]) + __uint_as_float(u[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(t[i]), 6);
+        if (on) {
+#pragma unroll
+          for (int m = 0; m < 6; ++m)
+            sts128(srow + (2 * fp + m / 3) * 1152 + (m % 3) * 16, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
         }
       }
       tc_fence_before();
-      mbar_arrive(d2empty);
+      mbar_arrive(d2empty(b));
       tick(2);
-      asm volatile("bar.sync 2, 96;" ::: "memory");  // staging tiles written
-#pragma unroll
-      for (int k = 0; k < FB * 72 / 96; ++k) {
-        const uint32_t so = stg0 + (dt + 96 * k) * 16;
-        const float4 x = lds128(so), y = lds128(so + C_::STG_BYTES), z = lds128(so + 2 * C_::STG_BYTES);
-        sts128(so, make_float4(x.x + y.x + z.x, x.y + y.y + z.y, x.z + y.z + z.z, x.w + y.w + z.w));
-      }
       fence_proxy_async_smem();
-      asm volatile("bar.sync 2, 96;" ::: "memory");  // slab complete (and tiles 1, 2 free again)
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // slab complete
       if (dt == 0 && !(a.ablate & 1)) {
         const int n0 = group_of(gi) * FB;
-        bulk_reduce_add_f32(a.dA + (size_t)n0 * 288, stg0, (uint32_t)min(FB, a.N - n0) * 1152u);
+        bulk_reduce_add_f32(a.dA + (size_t)n0 * 288, slab, (uint32_t)min(FB, a.N - n0) * 1152u);
         bulk_commit();
       }
       tick(3);
     }
-    if (lane == 0) bulk_wait_all();
-    if (dw == 0) tick_flush(3);
+    if (dt == 0) bulk_wait_all();
+    if (warp == W_DRAIN) tick_flush(3);
   } else if (warp == W_LOAD) {
     // ------------------------------------------------------------------ input loader
     for (int gi = 0; gi < ng; ++gi) {
@@ -699,12 +717,28 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
 #pragma unroll
     for (int c = 0; c < 3; ++c) bs[c] = __ldg(a.base + c * VP + v);
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    // G addresses: row = half*24 + f*12 + q (q = r*4 + c), k = lane.  The swizzle phase row & 7 = ((f&1)*4 + q) & 7
-    // is a compile-time constant per (f, q): eight lane-dependent offsets cover every store
-    const uint32_t gt = sbase + C_::OFF_G + wq * C_::GT_KB_BYTES + half * (FH * 12 * 128) + ((lane & 3) << 2);
-    uint32_t xo[8];
+    // G addresses.  16-byte unit u = 3 * (frame slot) + r holds [dv_r p0, dv_r p1, dv_r p2, dv_r]: n block u >> 3,
+    // 32-byte chunk (u >> 1) & 3 stored at chunk position ^ (k & 3), half u & 1.  This thread owns units 6*half ..
+    // 6*half+5 = three chunks; within a chunk the lanes with bit 2 set store the odd unit first, so the eight lanes
+    // of a store phase cover all eight 16-byte slots of the 128-byte bank window (conflict free).  One 16-byte store
+    // per unit and part: a quarter of the LSU instructions of a K-major G (the LSU instruction rate, ~0.5 / cycle, is
+    // what the workers run into once the accumulator is double buffered).
+    const bool swp = (lane >> 2) & 1;
+    uint32_t gx[3], gy[3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xo[i] = gt + ((((lane >> 2) ^ i) & 7) << 4);
+    for (int pl = 0; pl < 3; ++pl) {
+      const int p = 3 * half + pl;
+      const uint32_t cb = sbase + C_::OFF_G + (p >> 2) * C_::GQ_BYTES + (wq * 32 + lane) * 128 +
+                          ((((p & 3) ^ lane) & 3) << 5);
+      gx[pl] = cb + (swp ? 16u : 0u);
+      gy[pl] = cb + (swp ? 0u : 16u);
+    }
+    auto put = [&](uint32_t addr, float d, float p0, float p1, float p2) {
+      const float4 g = make_float4(d * p0, d * p1, d * p2, d);
+      sts128(addr, g);
+      sts128(addr + C_::GT_LO,
+             make_float4(g.x - trunc_tf32(g.x), g.y - trunc_tf32(g.y), g.z - trunc_tf32(g.z), g.w - trunc_tf32(g.w)));
+    };
     const unsigned lbit = 1u << lane;
     const float sp = a.sign_scale, sn = -a.sign_scale;
 
@@ -792,20 +826,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
       tick(4);
       if (gi > 0) mbar_wait(gfree(wq), (gi - 1) & 1);
       tick(5);
-      if (!(a.ablate & 2))
-#pragma unroll
-      for (int f = 0; f < FH; ++f) {
-        const float ph[3] = {bs[0] + po[f][0], bs[1] + po[f][1], bs[2] + po[f][2]};
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int q = r * 4 + c;
-            const float g = c < 3 ? dv[f][r] * ph[c] : dv[f][r];
-            const uint32_t off = xo[((f & 1) * 4 + q) & 7] + (f * 12 + q) * 128;
-            sts32(off, g);
-            sts32(off + C_::GT_LO, g - trunc_tf32(g));
-          }
+      if (!(a.ablate & 2)) {
+        const float p0[3] = {bs[0] + po[0][0], bs[1] + po[0][1], bs[2] + po[0][2]};
+        const float p1[3] = {bs[0] + po[1][0], bs[1] + po[1][1], bs[2] + po[1][2]};
+        // chunk 0: units (f0,r0) | (f0,r1); chunk 1: (f0,r2) | (f1,r0); chunk 2: (f1,r1) | (f1,r2)
+        put(gx[0], swp ? dv[0][1] : dv[0][0], p0[0], p0[1], p0[2]);
+        put(gy[0], swp ? dv[0][0] : dv[0][1], p0[0], p0[1], p0[2]);
+        put(gx[1], swp ? dv[1][0] : dv[0][2], swp ? p1[0] : p0[0], swp ? p1[1] : p0[1], swp ? p1[2] : p0[2]);
+        put(gy[1], swp ? dv[0][2] : dv[1][0], swp ? p0[0] : p1[0], swp ? p0[1] : p1[1], swp ? p0[2] : p1[2]);
+        put(gx[2], swp ? dv[1][2] : dv[1][1], p1[0], p1[1], p1[2]);
+        put(gy[2], swp ? dv[1][1] : dv[1][2], p1[0], p1[1], p1[2]);
       }
       fence_proxy_async_smem();
       mbar_arrive(gfull(wq));
@@ -898,7 +928,7 @@ int launch_bwd_timing(SkinBwdArgs a, cudaStream_t s) {
       {"inputs (ring)", "signs", "wait tfull", "tmem ld", "dPO", "wait gfree", "G phase", "-"},
       {"wait amfree", "Amat store", "fetch", "-", "-", "-", "-", "-"},
       {"wait gfull0", "wait gfull1", "wait gfull2", "wait gfull3", "mma0", "mma1", "mma2", "mma3"},
-      {"wait d2full", "wait slab read", "copy", "sum + bulk reduce", "-", "-", "-", "-"},
+      {"wait d2full", "wait slab free", "copy + sum", "bulk reduce", "-", "-", "-", "-"},
       {"-", "-", "-", "-", "-", "-", "-", "-"}};
   const double per[5] = {(double)NWORK, 1.0, 1.0, 1.0, 1.0};  // warps per role
   for (int r = 0; r < 5; ++r) {
