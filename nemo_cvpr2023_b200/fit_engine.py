@@ -135,6 +135,11 @@ class FitEngine:
         self.betas = torch.zeros(1, 10, device=self.dev)
         self.betas_grad = torch.zeros(1, 10, device=self.dev)
         self.compute_betas_grad = False
+        # the 2-D branch of a step (joint read-outs -> projection -> keypoint loss and its backward down to dR) is a chain
+        # of small, latency-bound kernels that is independent of the prior branch (VPoser, two meshes, GMM) until the
+        # gradients meet at the pose head: it runs on a side stream and fills the SMs the big kernels leave idle
+        self.overlap_2d = True
+        self._side = None
         self.centres = torch.linspace(0, 1, max(self.D, 1), device=self.dev)
         mv = self.g_motion.views
         o0 = self.g_motion.offsets['learned_motion.rot_out.weight'][0]
@@ -224,7 +229,7 @@ class FitEngine:
         w = dict(
             raw=z(N), X=z(Np, self.ldx), warped=z(N), yn=z(self.V, 3),
             H1=z(Np, h), H2=z(Np, h), H3=z(Np, h), Y=z(Np, LDY),
-            R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, LDF),
+            R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, LDF), F_m=z(N, LDF),
             PO_m=z(N, 3 * VP), PO_o=z(N, 3 * VP), PO_r=z(N, 3 * VP), dPO=z(N, 3 * VP),
             A_m=z(N, 288), A_o=z(N, 288), A_r=z(N, 288), JP=z(N, 72), JPs=z(N, 72),
             R_o=z(N, 24, 9), R_r=z(N, 24, 9),
@@ -234,7 +239,7 @@ class FitEngine:
             ll=z(N), acc=z(8), terms=z(8), wts=z(8), total=z(1),
             d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dAs=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
             dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, LDY), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.ldx),
-            dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dbase=z(3 * VP),
+            dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dJ_m=z(72), dbase=z(3 * VP),
             base=z(3, VP), J=z(72), vi=torch.zeros(N, dtype=torch.long, device=d),
             fi=torch.zeros(N, dtype=torch.long, device=d), noise=z(N, max(self.Cc, 1)),
         )
@@ -287,10 +292,10 @@ class FitEngine:
         which contract the pose feature with pre-reduced blend shapes -- identical arithmetic up to fp32 summation
         order, without the 6890-vertex mesh, its 20736-wide pose-blend GEMM or the skinning kernel."""
         C, ro = self.C_, self.ro
-        lib.pose_feature(w['R'], w['F'], LDF, N)
+        lib.pose_feature(w['R'], w['F_m'], LDF, N)   # own buffer: the prior branch rewrites w['F'] concurrently
         lib.chain_fwd(w['R'], w['J'], 0, C.parents, w['A_m'], w['JP'], N)
         if ro['np'] + ro['nx']:
-            gemm(w['F'], ro['MZ'], w['Z'], N, ro['ldz'], 207, LDF, ro['ldz'], ro['ldz'], bias=w['zb'])
+            gemm(w['F_m'], ro['MZ'], w['Z'], N, ro['ldz'], 207, LDF, ro['ldz'], ro['ldz'], bias=w['zb'])
             lib.readout_fwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['JX'], N)
 
     # ------------------------------------------------------------------ the step
@@ -320,12 +325,58 @@ class FitEngine:
         cx, cy = float(self.IMG_D0 // 2), float(self.IMG_D1 // 2)   # (:3104-3106) height/2 is used as cx
         ls = self.loss_scale
         acc = w['acc']   # 0 l1_sum, 1 kl_sum, 2 loss_3d, 3 gmm_sum, 4 kp, 5 instance
-        if need_2d:
+        dR = w['dR']
+
+        def branch_2d_forward():
             self._joints_forward(w, N)
             lib.joints_gather_fwd(w['JP'], w['JX'], ro['np'] + ro['nx'], ro['np'], self.map25, 25, w['trans'], None,
                                   w['j25'], N)
             lib.kp_loss_fwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox, self.focal,
                             cx, cy, 100.0, mode_id, red, w['p2d'], w['loss_all'], w['view_acc'], N, 25, self.V, self.F)
+
+        def branch_2d_backward():
+            lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox,
+                            self.focal, cx, cy, 100.0, mode_id, red, w['view_acc'], ls, w['dj25'], w['dcam'].zero_(),
+                            acc[4:5], N, 25, self.V, self.F)
+            lib.cam_finish(self.g_cam.views['learned_cameras'], w['dcam'], self.g_cam.gviews['learned_cameras'],
+                           0, self.V)
+            lib.joints_gather_bwd(w['dj25'], ro['np'] + ro['nx'], ro['np'], self.map25, 25, None, w['dJP'],
+                                  w['dJX'], w['dtr'], N)
+            nq = ro['np'] + ro['nx']
+            if nq:
+                lib.readout_bwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['dJX'],
+                                w['dA'], 0, w['dZ'], N)
+            lib.chain_bwd(w['R'], w['J'], 0, C.parents, w['dA'] if nq else None, None, w['dJP'], dR,
+                          w['dJ_m'].zero_(), N)
+            if detach_pose:
+                # V4 opt_cam (:4060-4149): body rotmats detached, gradient reaches the MLP through the global
+                # orientation and the translation only
+                dR[:, 1:].zero_()
+            elif nq:
+                gemm(w['dZ'], ro['MZ'], dR.view(-1)[9:], N, 207, ro['ldz'], ro['ldz'], ro['ldz'], 216, transB=True,
+                     accumulate=True)
+            if self.compute_betas_grad:
+                w['dJ'].copy_(w['dJ_m'])
+                self._betas_grad(w, N, first=True, mesh=False)
+
+        # fork: with both branches present (a full step that updates), the 2-D branch goes to the side stream
+        overlap = (self.overlap_2d and need_2d and mode == 'step' and update and not self.compute_betas_grad
+                   and lib.profile is None)
+        if update:
+            for g in self.groups():
+                g.g.zero_()
+        if overlap:
+            if self._side is None:
+                self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Event(), torch.cuda.Event())
+            side, ev_fork, ev_join = self._side
+            ev_fork.record()
+            side.wait_event(ev_fork)
+            with torch.cuda.stream(side):
+                branch_2d_forward()
+                branch_2d_backward()
+                ev_join.record(side)
+        elif need_2d:
+            branch_2d_forward()
         w_vp = float(a.weight_vp_loss) if full else 0.0
         w_kl = float(a.weight_vp_z_loss) if full else 0.0
         w_gmm = float(a.weight_gmm_loss) if full else 0.0
@@ -369,32 +420,9 @@ class FitEngine:
 
         # ---------------------------------------------------------------- backward
         if update:
-            for g in self.groups():
-                g.g.zero_()
-            dR = w['dR']
             if need_2d:
-                lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox,
-                                self.focal, cx, cy, 100.0, mode_id, red, w['view_acc'], ls, w['dj25'], w['dcam'].zero_(),
-                                acc[4:5], N, 25, self.V, self.F)
-                lib.cam_finish(self.g_cam.views['learned_cameras'], w['dcam'], self.g_cam.gviews['learned_cameras'],
-                               0, self.V)
-                lib.joints_gather_bwd(w['dj25'], ro['np'] + ro['nx'], ro['np'], self.map25, 25, None, w['dJP'],
-                                      w['dJX'], w['dtr'], N)
-                nq = ro['np'] + ro['nx']
-                if nq:
-                    lib.readout_bwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['dJX'],
-                                    w['dA'], 0, w['dZ'], N)
-                lib.chain_bwd(w['R'], w['J'], 0, C.parents, w['dA'] if nq else None, None, w['dJP'], dR,
-                              w['dJ'].zero_(), N)
-                if detach_pose:
-                    # V4 opt_cam (:4060-4149): body rotmats detached, gradient reaches the MLP through the global
-                    # orientation and the translation only
-                    dR[:, 1:].zero_()
-                elif nq:
-                    gemm(w['dZ'], ro['MZ'], dR.view(-1)[9:], N, 207, ro['ldz'], ro['ldz'], ro['ldz'], 216, transB=True,
-                         accumulate=True)
-                if self.compute_betas_grad:
-                    self._betas_grad(w, N, first=True, mesh=False)
+                if not overlap:
+                    branch_2d_backward()
             else:
                 dR.zero_()
                 w['dtr'].zero_()
@@ -413,7 +441,11 @@ class FitEngine:
                     self._betas_grad(w, N, first=not need_2d, mesh=True)
                 lib.rodrigues_bwd(w['aa'].view(-1)[3:], 72, w['dR_o'].view(-1)[9:], 216, w['d_aa'].view(-1)[3:], 72,
                                   23, 1, N * 23, 0)
+                if overlap:
+                    torch.cuda.current_stream().wait_event(ev_join)
                 dR[:, 0].add_(w['dR_o'][:, 0])
+            elif overlap:
+                torch.cuda.current_stream().wait_event(ev_join)
             # axis-angle outputs of the pose head -> rotation matrices -> 6D -> MLP output
             lib.rotmat2aa_bwd(w['R'], 9, w['d_aa'], 3, dR, 9, 1, 1, N * 24, 1)
             w['dY'].zero_()
@@ -518,7 +550,7 @@ class FitEngine:
         V = None
         if want_vertices:
             V = torch.empty(N, NV, 3, device=self.dev)
-            gemm(w['F'], C.PD, w['PO_m'], N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
+            gemm(w['F_m'], C.PD, w['PO_m'], N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
             lib.skin_fwd(w['A_m'], w['PO_m'], w['base'], C.Wt, V, N)
         j = torch.empty(N, 25, 3, device=self.dev)
         lib.joints_gather_fwd(w['JP'], w['JX'], ro['np'] + ro['nx'], ro['np'], self.map25, 25,
