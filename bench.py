@@ -213,6 +213,7 @@ def run_gpu(a):
     dev = 'cuda:%d' % local
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries ONE JSON line, nothing else
         dist.init_process_group('nccl', device_id=torch.device(dev))
     from nemo_cvpr2023_b200._lib import lib
     from nemo_cvpr2023_b200.nemo import neural_motion_model as nmm
