@@ -213,8 +213,19 @@ def run_gpu(a):
     dev = 'cuda:%d' % local
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries ONE JSON line, nothing else
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+        # stdout carries ONE JSON line and nothing else: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        # (set in this image), so file descriptor 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device(dev))
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from nemo_cvpr2023_b200._lib import lib
     from nemo_cvpr2023_b200.nemo import neural_motion_model as nmm
     from nemo_cvpr2023_b200.nemo.multi_view_sequence import SyntheticMultiViewSequence
