@@ -262,6 +262,27 @@ int nemo_b200_adam(float* p, const float* g, float* m, float* v, size_t n, float
                    void* stream);
 int nemo_b200_increment(int* counter, void* stream);   /* *counter += 1 on the device */
 
+/* Every optimiser of a fit model in ONE launch (the reference steps 3-4 torch.optim.Adam objects per iteration,
+ * nemo/neural_motion_model.py:3586-3588, each a Python loop over parameter tensors).  A segment = a 16-byte aligned
+ * range of a flat parameter buffer with its own hyper-parameters and a DEVICE count of completed steps (`step`;
+ * segments may share one counter, exactly one of them carries OWNS_STEP).  The kernel uses *step + 1 as the step
+ * number and advances the counters itself (no increment kernel; safe under CUDA-graph replay).  SKIP leaves the
+ * segment and its counter untouched: torch.optim.Adam skips parameters whose .grad is None (the warm-up phase never
+ * reaches linear_out.*, :3455-3509).  `segs` is a HOST array, copied into the launch parameters; `ticket` is a device
+ * int that must be 0 on entry (the kernel resets it). */
+#define NEMO_B200_ADAM_MAX_SEGS 16
+#define NEMO_B200_ADAM_SKIP 1
+#define NEMO_B200_ADAM_OWNS_STEP 2
+typedef struct nemo_b200_adam_seg {
+  float* p; const float* g; float* m; float* v;
+  unsigned long long n;
+  float lr, beta1, beta2, eps, weight_decay;
+  int decoupled;   /* 0: torch.optim.Adam (L2 in the gradient), 1: AdamW */
+  int* step;
+  int flags;
+} nemo_b200_adam_seg;
+int nemo_b200_adam_multi(const nemo_b200_adam_seg* segs, int nseg, int* ticket, void* stream);
+
 /* small utilities used by the host mirror */
 /* out = dy * act'(y) for y = act(.), act 1 relu / 2 leaky_relu(0.01) */
 int nemo_b200_act_bwd(const float* dy, const float* y, float* out, size_t n, int act, void* stream);

@@ -120,6 +120,23 @@ def _arg(x):
 lib = _Lib()
 
 
+class AdamSeg(ctypes.Structure):
+    """nemo_b200_adam_seg (include/nemo_b200.h)."""
+    _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p),
+                ('n', ctypes.c_ulonglong), ('lr', ctypes.c_float), ('beta1', ctypes.c_float), ('beta2', ctypes.c_float),
+                ('eps', ctypes.c_float), ('weight_decay', ctypes.c_float), ('decoupled', ctypes.c_int),
+                ('step', ctypes.c_void_p), ('flags', ctypes.c_int)]
+
+
+ADAM_SKIP, ADAM_OWNS_STEP, ADAM_MAX_SEGS = 1, 2, 16
+
+
+def adam_multi(segs, ticket):
+    """segs: list of AdamSeg; one launch of nemo_b200_adam_multi on the current stream."""
+    arr = (AdamSeg * len(segs))(*segs)
+    lib.adam_multi(ctypes.addressof(arr), len(segs), ticket)
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError('nemo_cvpr2023_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')

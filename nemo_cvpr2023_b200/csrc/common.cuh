@@ -52,6 +52,35 @@ void set_error(const char* fmt, ...);
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-device caches (an engine may live on any device of the process): SM count, and "this kernel's dynamic shared
+// memory attribute has been set on this device".
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < MAX_DEVICES ? dev : 0;
+}
+inline int num_sms() {
+  static int n[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v;
+  }
+  return n[dev];
+}
+// once per (kernel, device)
+#define NB_SET_SMEM_ONCE(kernel, bytes)                                                              \
+  do {                                                                                               \
+    static bool done__[nb::MAX_DEVICES] = {false};                                                   \
+    const int dev__ = nb::current_device();                                                          \
+    if (!done__[dev__]) {                                                                            \
+      NB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));   \
+      done__[dev__] = true;                                                                          \
+    }                                                                                                \
+  } while (0)
+
 constexpr int NV = NEMO_B200_NV;
 constexpr int VP = NEMO_B200_VP;
 constexpr int NJ = NEMO_B200_NJ;

@@ -444,23 +444,9 @@ int make_map(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer,
   return 0;
 }
 
-int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
-}
-
 template <bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    NB_CUDA(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
+  NB_SET_SMEM_ONCE((k_gemm_tc<A_MN, B_MN>), SMEM_BYTES);
   k_gemm_tc<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
   NB_LAUNCH_CHECK("gemm_tc");
 }

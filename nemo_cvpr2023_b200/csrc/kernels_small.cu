@@ -1020,6 +1020,72 @@ extern "C" int nemo_b200_increment(int* counter, void* stream) {
   k_increment<<<1, 1, 0, S(stream)>>>(counter);
   NB_LAUNCH_CHECK("increment");
 }
+
+// One launch for every optimiser of a fit model (the reference steps 3-4 torch.optim.Adam instances, each a loop over
+// its parameter tensors: nemo/neural_motion_model.py:3586-3588).  A segment is a contiguous range of one flat parameter
+// buffer with its own hyper-parameters and a device-resident count of COMPLETED steps; segments may share a counter.
+// Every block reads `*step + 1` as the current step; the counters are advanced by the last block to finish (ticket),
+// so no block can see the incremented value and no separate increment kernel is needed.  Segments flagged SKIP are
+// left untouched and their counter is not advanced -- torch.optim.Adam skips parameters whose grad is None
+// (warm-up leaves linear_out.* without gradient, :3455-3509).
+struct AdamTable {
+  nemo_b200_adam_seg seg[NEMO_B200_ADAM_MAX_SEGS];
+  int first_block[NEMO_B200_ADAM_MAX_SEGS + 1];
+  int nseg;
+};
+__global__ void k_adam_multi(const __grid_constant__ AdamTable t, int* __restrict__ ticket) {
+  int s = 0;
+  while (s + 1 < t.nseg && (int)blockIdx.x >= t.first_block[s + 1]) ++s;
+  const nemo_b200_adam_seg& sg = t.seg[s];
+  const size_t i0 = ((size_t)(blockIdx.x - t.first_block[s]) * blockDim.x + threadIdx.x) * 4;
+  if (!(sg.flags & NEMO_B200_ADAM_SKIP) && i0 < sg.n) {
+    const float step = (float)(*sg.step + 1);
+    const float bc1 = 1.f - powf(sg.beta1, step), bc2s = sqrtf(1.f - powf(sg.beta2, step));
+    if (i0 + 4 <= sg.n) {  // segments start on 16-byte boundaries (ParamGroup rounds every tensor up to 4 floats)
+      float4 p = *reinterpret_cast<float4*>(sg.p + i0), m = *reinterpret_cast<float4*>(sg.m + i0),
+             v = *reinterpret_cast<float4*>(sg.v + i0);
+      const float4 g = *reinterpret_cast<const float4*>(sg.g + i0);
+      adam_elem(&p.x, g.x, &m.x, &v.x, sg.lr, sg.beta1, sg.beta2, sg.eps, sg.weight_decay, sg.decoupled, bc1, bc2s);
+      adam_elem(&p.y, g.y, &m.y, &v.y, sg.lr, sg.beta1, sg.beta2, sg.eps, sg.weight_decay, sg.decoupled, bc1, bc2s);
+      adam_elem(&p.z, g.z, &m.z, &v.z, sg.lr, sg.beta1, sg.beta2, sg.eps, sg.weight_decay, sg.decoupled, bc1, bc2s);
+      adam_elem(&p.w, g.w, &m.w, &v.w, sg.lr, sg.beta1, sg.beta2, sg.eps, sg.weight_decay, sg.decoupled, bc1, bc2s);
+      *reinterpret_cast<float4*>(sg.p + i0) = p;
+      *reinterpret_cast<float4*>(sg.m + i0) = m;
+      *reinterpret_cast<float4*>(sg.v + i0) = v;
+    } else {
+      for (size_t i = i0; i < sg.n; ++i)
+        adam_elem(sg.p + i, sg.g[i], sg.m + i, sg.v + i, sg.lr, sg.beta1, sg.beta2, sg.eps, sg.weight_decay,
+                  sg.decoupled, bc1, bc2s);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+      for (int k = 0; k < t.nseg; ++k)
+        if ((t.seg[k].flags & NEMO_B200_ADAM_OWNS_STEP) && !(t.seg[k].flags & NEMO_B200_ADAM_SKIP)) *t.seg[k].step += 1;
+      *ticket = 0;
+    }
+  }
+}
+extern "C" int nemo_b200_adam_multi(const nemo_b200_adam_seg* segs, int nseg, int* ticket, void* stream) {
+  NB_REQUIRE(segs && ticket && nseg > 0 && nseg <= NEMO_B200_ADAM_MAX_SEGS, "adam_multi: 1..%d segments",
+             NEMO_B200_ADAM_MAX_SEGS);
+  AdamTable t;
+  t.nseg = nseg;
+  int blocks = 0;
+  for (int s = 0; s < nseg; ++s) {
+    NB_REQUIRE(segs[s].p && segs[s].g && segs[s].m && segs[s].v && segs[s].step, "adam_multi: null buffer in segment %d", s);
+    NB_REQUIRE(((uintptr_t)segs[s].p % 16 == 0) && ((uintptr_t)segs[s].g % 16 == 0) && ((uintptr_t)segs[s].m % 16 == 0) &&
+               ((uintptr_t)segs[s].v % 16 == 0), "adam_multi: segment %d is not 16-byte aligned", s);
+    t.seg[s] = segs[s];
+    t.first_block[s] = blocks;
+    blocks += max(1, cdiv((long long)segs[s].n, 1024));
+  }
+  t.first_block[nseg] = blocks;
+  k_adam_multi<<<blocks, 256, 0, S(stream)>>>(t, ticket);
+  NB_LAUNCH_CHECK("adam_multi");
+}
 __global__ void k_scale_add(float* __restrict__ y, const float* __restrict__ x, float a, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] += a * x[i];

@@ -857,16 +857,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   }
 }
 
-int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
-}
-
 // Frame groups per CTA.  Every CTA pays a set-up (W operands into shared / tensor memory) worth `setup` groups, and
 // the grid runs in waves over 148 x ctas_per_sm slots: pick the chunk count that minimises waves x (groups + set-up).
 void chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int max_chunks, int& groups_per_chunk,
@@ -890,23 +880,14 @@ void chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int ma
 
 template <int MODE>
 int launch_fwd(const SkinArgs& a, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    NB_CUDA(cudaFuncSetAttribute(k_skin_tc_fwd<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg::SMEM_BYTES));
-    configured = true;
-  }
+  NB_SET_SMEM_ONCE(k_skin_tc_fwd<MODE>, FwdCfg::SMEM_BYTES);
   k_skin_tc_fwd<MODE><<<NT_V * a.nchunks, FWD_THREADS, FwdCfg::SMEM_BYTES, s>>>(a);
   NB_LAUNCH_CHECK("skin_tc_fwd");
 }
 
 template <bool HAS_DV, bool HAS_SIGNS>
 int launch_bwd_plain(const SkinBwdArgs& a, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    NB_CUDA(cudaFuncSetAttribute(k_skin_tc_bwd<HAS_DV, HAS_SIGNS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 BwdCfg::SMEM_BYTES));
-    configured = true;
-  }
+  NB_SET_SMEM_ONCE((k_skin_tc_bwd<HAS_DV, HAS_SIGNS>), BwdCfg::SMEM_BYTES);
   k_skin_tc_bwd<HAS_DV, HAS_SIGNS><<<NT_V * a.nchunks, BWD_THREADS, BwdCfg::SMEM_BYTES, s>>>(a);
   NB_LAUNCH_CHECK("skin_tc_bwd");
 }

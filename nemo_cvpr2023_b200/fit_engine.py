@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import assets
-from ._lib import lib, require_cuda
+from ._lib import ADAM_OWNS_STEP, ADAM_SKIP, AdamSeg, adam_multi, lib, require_cuda
 from .functional import KP_LOSSES, NV, RBF_BASES, VP, SMPLConstants, gemm
 
 LDY = 148      # row stride of the (N+1, 147) MLP output / its gradient: 16-byte rows for the TMA-fed GEMM
@@ -68,10 +68,71 @@ class ParamGroup:
             self.offsets[name] = (o, k)
             o += size
 
-    def adam_step(self):
-        lib.increment(self.step_dev)
-        lib.adam(self.p, self.g, self.m, self.v, self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                 self.wd, int(self.decoupled), 0, self.step_dev)
+    def set_lagging(self, names):
+        """Tensors the reference's warm-up never reaches (grad None -> torch.optim.Adam keeps no state for them and
+        their per-parameter step count lags, nemo/neural_motion_model.py:3455-3509): they get their own device step
+        counter and can be skipped by `adam_step(skip_lag=True)`."""
+        self.lag_names = [n for n in names if n in self.offsets]
+        self.step_lag_dev = torch.zeros(1, dtype=torch.int32, device=self.p.device)
+
+    def ranges(self):
+        """[(offset, size, lagging)] covering the flat buffer, maximal runs of equal class."""
+        lag = set(getattr(self, 'lag_names', ()))
+        if not lag:
+            return [(0, self.p.numel(), False)]
+        names = [sp[0] for sp in self.specs]
+        starts = [self.offsets[n][0] for n in names] + [self.p.numel()]
+        out = []
+        for i, n in enumerate(names):
+            cls = n in lag
+            if out and out[-1][2] == cls:
+                out[-1] = (out[-1][0], starts[i + 1] - out[-1][0], cls)
+            else:
+                out.append((starts[i], starts[i + 1] - starts[i], cls))
+        return out
+
+    def segments(self, skip_lag=False):
+        segs, owned = [], set()
+        for o, k, lagging in self.ranges():
+            step = self.step_lag_dev if lagging else self.step_dev
+            flags = 0
+            if step.data_ptr() not in owned:
+                flags |= ADAM_OWNS_STEP
+                owned.add(step.data_ptr())
+            if lagging and skip_lag:
+                flags |= ADAM_SKIP
+            segs.append(AdamSeg(self.p.data_ptr() + 4 * o, self.g.data_ptr() + 4 * o, self.m.data_ptr() + 4 * o,
+                                self.v.data_ptr() + 4 * o, k, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                int(self.decoupled), step.data_ptr(), flags))
+        return segs
+
+    def adam_step(self, skip_lag=False):
+        if not hasattr(self, 'ticket'):
+            self.ticket = torch.zeros(1, dtype=torch.int32, device=self.p.device)
+        adam_multi(self.segments(skip_lag), self.ticket)
+
+    def reset_state(self):
+        self.m.zero_(), self.v.zero_(), self.step_dev.zero_()
+        if hasattr(self, 'step_lag_dev'):
+            self.step_lag_dev.zero_()
+
+
+def motion_specs(h, in_dim, ldx, D):
+    """Layout of the opt_motion buffer (MotionNet + RBF log_sigmas, nemo/neural_motion_model.py:3694-3711).  The two
+    output heads are adjacent -- [rot_out.weight; linear_out.weight] is the (147, h) operand of ONE head GEMM, and
+    [rot_out.bias; linear_out.bias] its bias -- and the first layer's rows are padded to 16 bytes for the TMA-fed GEMM,
+    so the flat order is NOT torch's parameter order; FusedAdam maps between the two."""
+    specs = [('learned_motion.net.net.0.weight', (h, in_dim), ldx), ('learned_motion.net.net.0.bias', (h,)),
+             ('learned_motion.net.net.2.weight', (h, h)), ('learned_motion.net.net.2.bias', (h,)),
+             ('learned_motion.net.net.4.weight', (h, h)), ('learned_motion.net.net.4.bias', (h,)),
+             ('learned_motion.rot_out.weight', (144, h)), ('learned_motion.linear_out.weight', (3, h)),
+             ('learned_motion.rot_out.bias', (144,)), ('learned_motion.linear_out.bias', (3,))]
+    if D > 0:
+        specs.append(('phase_rbf.log_sigmas', (D,)))
+    return specs
+
+
+LAGGING = ['learned_motion.linear_out.weight', 'learned_motion.linear_out.bias']
 
 
 def fold_vposer(sd, device):
@@ -103,6 +164,18 @@ def fold_vposer(sd, device):
                 Wd5=f(g('decoder_net.5.weight')), bd5=f(g('decoder_net.5.bias')))
 
 
+def _on_device(fn):
+    """Run an engine method with the engine's device current (streams, events and the library's per-device state
+    are created against the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 class FitEngine:
     def __init__(self, args, num_views, num_frames, smpl_consts: SMPLConstants, vposer_sd, gmm, data,
                  version=2, device='cuda', init_params=None, focal=assets.FOCAL_LENGTH):
@@ -122,14 +195,9 @@ class FitEngine:
         h, V, K = self.h, self.V, self.K
         # ---- parameters, grouped as the reference groups its optimisers
         self.g_cam = ParamGroup([('learned_cameras', (V, 9))], self.dev, a.lr_camera)
-        motion = [('learned_motion.net.net.0.weight', (h, self.in_dim), self.ldx), ('learned_motion.net.net.0.bias', (h,)),
-                  ('learned_motion.net.net.2.weight', (h, h)), ('learned_motion.net.net.2.bias', (h,)),
-                  ('learned_motion.net.net.4.weight', (h, h)), ('learned_motion.net.net.4.bias', (h,)),
-                  ('learned_motion.rot_out.weight', (144, h)), ('learned_motion.linear_out.weight', (3, h)),
-                  ('learned_motion.rot_out.bias', (144,)), ('learned_motion.linear_out.bias', (3,))]
-        if self.D > 0:
-            motion.append(('phase_rbf.log_sigmas', (self.D,)))
+        motion = motion_specs(h, self.in_dim, self.ldx, self.D)
         self.g_motion = ParamGroup(motion, self.dev, a.lr_human, a.wd_human, decoupled=(a.opt_human == 'adamw'))
+        self.g_motion.set_lagging(LAGGING)
         self.g_phase = ParamGroup([('shifts', (V, K)), ('scales', (V, K))], self.dev, a.lr_phase)
         self.g_inst = ParamGroup([('learned_instance_code', (V, self.Cc))], self.dev, a.lr_instance) if self.Cc else None
         self.betas = torch.zeros(1, 10, device=self.dev)
@@ -299,6 +367,7 @@ class FitEngine:
             lib.readout_fwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['JX'], N)
 
     # ------------------------------------------------------------------ the step
+    @_on_device
     def forward_backward(self, view_idx, frame_idx, update=True, phases=None, mode='step', detach_pose=False):
         """mode: 'step' (all losses), 'warmup' (3D pose loss only), 'opt_cam' (V4: 2D + 3D, pose detached),
         'cam_fit' (MultiViewModel.opt_cam: plain-mean reprojection loss only)."""
@@ -517,9 +586,15 @@ class FitEngine:
                       gg['scales'], self.g_inst.gviews['learned_instance_code'] if self.g_inst else None, w['gy01'], N,
                       self.V)
 
-    def optimizer_step(self, which=None):
+    @_on_device
+    def optimizer_step(self, which=None, skip_lag=False):
+        """Adam / AdamW of every optimiser in ONE launch (nemo_b200_adam_multi)."""
+        segs = []
         for g in (which or self.groups()):
-            g.adam_step()
+            segs += g.segments(skip_lag)
+        if not hasattr(self, '_adam_ticket'):
+            self._adam_ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        adam_multi(segs, self._adam_ticket)
 
     # ------------------------------------------------------------------ read-backs
     def loss_dict(self, w, norm):
@@ -531,6 +606,7 @@ class FitEngine:
         return {k: np.asarray(v, dtype=np.float32) for k, v in d.items()}
 
     @torch.no_grad()
+    @_on_device
     def predict(self, view_idx, frame_idx, add_trans=True, phases=None, want_vertices=True):
         """get_preds_batch forward (:3637-3672): vertices (N,6890,3), the 25 loss joints, poses, orient, trans."""
         C = self.C_

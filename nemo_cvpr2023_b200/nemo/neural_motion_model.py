@@ -114,8 +114,10 @@ class MotionNet(nn.Module):
 
 
 class FusedAdam(torch.optim.Optimizer):
-    """torch.optim.Adam/AdamW-compatible handle (param_groups, state_dict, zero_grad, step) on one flat
-    engine buffer; `step()` is one launch of nemo_b200_adam."""
+    """torch.optim.Adam/AdamW-compatible handle (param_groups, state_dict, zero_grad, step) on one flat engine
+    buffer.  `state_dict()` / `load_state_dict()` speak torch.optim.Adam's own format (per-parameter `step`,
+    `exp_avg`, `exp_avg_sq`, in the reference's parameter order), so checkpoints move between the reference and this
+    mirror in both directions (`MultiViewModel.save/load`, nemo/neural_motion_model.py:257-280)."""
 
     def __init__(self, params, group, lr, weight_decay=0.0, decoupled=False):
         self._g = group
@@ -125,36 +127,64 @@ class FusedAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=False):
         self._g.g.zero_()
 
-    @torch.no_grad()
-    def step(self, closure=None):
+    def sync_hyper(self):
         pg = self.param_groups[0]
         self._g.lr, self._g.wd, self._g.betas, self._g.eps = pg['lr'], pg['weight_decay'], pg['betas'], pg['eps']
-        self._g.adam_step()
+
+    @torch.no_grad()
+    def step(self, closure=None, skip_lag=False):
+        self.sync_hyper()
+        self._g.adam_step(skip_lag=skip_lag)
+
+    # ---- the engine's storage of optimiser parameter i: (moment views, step counter)
+    def _slot(self, p):
+        g = self._g
+        off = (p.data_ptr() - g.p.data_ptr()) // 4
+        if not (0 <= off < g.p.numel()):
+            raise RuntimeError('optimizer parameter is not a view of the engine buffer')
+        m = torch.as_strided(g.m, p.shape, p.stride(), off)
+        v = torch.as_strided(g.v, p.shape, p.stride(), off)
+        lag = any(lo <= off < lo + k for lo, k, lagging in g.ranges() if lagging)
+        return m, v, (g.step_lag_dev if lag else g.step_dev)
 
     def state_dict(self):
         sd = super().state_dict()
-        sd['flat'] = dict(m=self._g.m.clone(), v=self._g.v.clone(), step=self._g.step_dev.clone())
+        state = {}
+        for i, p in enumerate(self.param_groups[0]['params']):
+            m, v, step = self._slot(p)
+            n = int(step.item())
+            if n > 0:   # torch.optim.Adam creates the state of a parameter at its first step with a gradient
+                state[i] = {'step': torch.tensor(float(n)), 'exp_avg': m.clone(), 'exp_avg_sq': v.clone()}
+        sd['state'] = state
+        sd['param_groups'][0].pop('decoupled', None)
         return sd
 
     def load_state_dict(self, sd):
-        flat = sd.get('flat')
-        if flat is not None:
-            self._g.m.copy_(flat['m'])
-            self._g.v.copy_(flat['v'])
-            self._g.step_dev.copy_(flat['step'])
-        else:  # a checkpoint written by the reference (torch.optim.Adam): per-parameter state
-            o = 0
+        g = self._g
+        if 'flat' in sd:   # round-1 format of this repo
+            g.m.copy_(sd['flat']['m']), g.v.copy_(sd['flat']['v']), g.step_dev.copy_(sd['flat']['step'])
+            if hasattr(g, 'step_lag_dev'):
+                g.step_lag_dev.copy_(sd['flat']['step'])
+        else:
+            g.reset_state()
+            steps = {}
             for i, p in enumerate(self.param_groups[0]['params']):
                 st = sd['state'].get(i)
-                k = p.numel()
-                if st is not None:
-                    self._g.m[o:o + k].copy_(st['exp_avg'].reshape(-1))
-                    self._g.v[o:o + k].copy_(st['exp_avg_sq'].reshape(-1))
-                    self._g.step_dev.fill_(int(st['step']))
-                o += k
-        for k in ('lr', 'weight_decay'):
-            if sd.get('param_groups'):
-                self.param_groups[0][k] = sd['param_groups'][0][k]
+                if st is None:
+                    continue
+                m, v, step = self._slot(p)
+                m.copy_(torch.as_tensor(st['exp_avg']).reshape(p.shape))
+                v.copy_(torch.as_tensor(st['exp_avg_sq']).reshape(p.shape))
+                n = int(st['step'])
+                if steps.setdefault(step.data_ptr(), n) != n:
+                    raise RuntimeError('checkpoint has per-parameter Adam step counts this engine cannot represent '
+                                       '(%d vs %d within one step class)' % (steps[step.data_ptr()], n))
+                step.fill_(n)
+        if sd.get('param_groups'):
+            for k in ('lr', 'weight_decay', 'betas', 'eps'):
+                if k in sd['param_groups'][0]:
+                    self.param_groups[0][k] = sd['param_groups'][0][k]
+        self.sync_hyper()
 
 
 class MultiViewModel(nn.Module):
@@ -488,8 +518,7 @@ class MultiViewModel(nn.Module):
         vi, fi = self._idx(view_idx), self._idx(frame_idx)
         w, norm = e.forward_backward(vi, fi, update=update, mode='step')
         if update:
-            for opt in self.optimizers:
-                opt.step()
+            self._step_optimizers()
         ld = e.loss_dict(w, norm)
         loss_dict = {k: ld[k] for k in self._LOSS_KEYS}
         if update and self.args.lr_factor < 1:
@@ -498,7 +527,19 @@ class MultiViewModel(nn.Module):
         info_dict = {'view_idx': w['vi'].clone(), 'frame_idx': w['fi'].clone(), 'loss_all': w['loss_all'].clone(),
                      'points2d_gt': self.points2d_gt_all[w['vi'], w['fi']]}
         self.training = False
+        e.training = False
         return loss_dict, info_dict
+
+    def _step_optimizers(self, which=None, skip_lag=False):
+        """`for opt in self.optimizers: opt.step()` (:3586-3588) as one launch over every flat buffer."""
+        opts = which if which is not None else self.optimizers
+        if all(isinstance(o, FusedAdam) for o in opts):
+            for o in opts:
+                o.sync_hyper()
+            self.engine.optimizer_step([o._g for o in opts], skip_lag=skip_lag)
+        else:
+            for o in opts:
+                o.step()
 
     def _sample(self):
         bs = self.args.batch_size
@@ -512,12 +553,13 @@ class MultiViewModel(nn.Module):
         if not self.args.batch_size > -1:
             raise NotImplementedError()
         e = self.engine
+        e.training = self.training
         losses = []
         for _ in range(warmup_steps):
             vi, fi = self._sample()
             w, _ = e.forward_backward(vi, fi, update=True, mode='warmup')
-            self.opt_motion.step()
-            self.opt_phase.step()
+            # linear_out.* get no gradient here: torch.optim.Adam skips them (no weight decay, no state, step stays 0)
+            self._step_optimizers([self.opt_motion, self.opt_phase], skip_lag=True)
             losses.append(w['acc'][2].clone())   # `acc` is a reused workspace slot
         return [float(x) for x in torch.stack(losses).cpu()]
 
@@ -525,13 +567,21 @@ class MultiViewModel(nn.Module):
         """:2869-2906: Adam on the cameras only, first frame of every view, plain-mean reprojection loss."""
         e = self.engine
         vi, fi = torch.arange(self.num_views), torch.zeros(self.num_views, dtype=torch.long)
-        e.g_cam.m.zero_(), e.g_cam.v.zero_(), e.g_cam.step_dev.zero_()   # the reference builds a fresh Adam here
-        e.g_cam.lr = self.args.lr_camera
+        e.training = self.training
+        # the reference builds a throw-away Adam here (:2873-2876): self.opt_cameras starts fresh afterwards, so the
+        # camera-fit moments live in temporary buffers and the real ones are untouched
+        g = e.g_cam
+        keep = (g.m, g.v, g.step_dev, g.lr)
+        g.m, g.v, g.step_dev = torch.zeros_like(g.m), torch.zeros_like(g.v), torch.zeros_like(g.step_dev)
+        g.lr = self.args.lr_camera
         log = []
-        for _ in range(cam_opt_steps):
-            w, _ = e.forward_backward(vi, fi, update=True, mode='cam_fit')
-            e.g_cam.adam_step()
-            log.append(w['acc'][4].clone())
+        try:
+            for _ in range(cam_opt_steps):
+                w, _ = e.forward_backward(vi, fi, update=True, mode='cam_fit')
+                g.adam_step()
+                log.append(w['acc'][4].clone())
+        finally:
+            g.m, g.v, g.step_dev, g.lr = keep
         return [np.asarray(x) for x in torch.stack(log).cpu().numpy()] if log else []
 
 
@@ -564,11 +614,11 @@ class NemoV4(NemoV3):
         if not self.args.batch_size > -1:
             raise NotImplementedError()
         e = self.engine
+        e.training = self.training
         for _ in range(cam_opt_steps):
             vi, fi = self._sample()
             e.forward_backward(vi, fi, update=True, mode='opt_cam', detach_pose=True)
-            for opt in self.optimizers:
-                opt.step()
+            self._step_optimizers()
 
 
 class NemoV0(MultiViewModel):

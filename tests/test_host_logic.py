@@ -1,0 +1,90 @@
+"""Host-side logic that needs no GPU: the optimiser-state mapping between torch.optim.Adam's per-parameter layout (what
+the reference's `save` writes, nemo/neural_motion_model.py:257-265) and the engine's flat, padded, head-adjacent
+buffers; the segment table of the fused Adam launch."""
+import os
+
+import numpy as np
+import torch
+
+from nemo_cvpr2023_b200 import fit_engine as fe
+from nemo_cvpr2023_b200.nemo.neural_motion_model import FusedAdam
+from oracle.make_golden import step_case
+from tests.util import GOLD
+
+
+def _motion_group(h, in_dim, D):
+    ldx = (in_dim + 3) // 4 * 4
+    g = fe.ParamGroup(fe.motion_specs(h, in_dim, ldx, D), 'cpu', 1e-3, 1e-3)
+    g.set_lagging(fe.LAGGING)
+    return g
+
+
+def _torch_order(g):
+    names = ['learned_motion.net.net.%d.%s' % (i, k) for i in (0, 2, 4) for k in ('weight', 'bias')]
+    names += ['learned_motion.rot_out.weight', 'learned_motion.rot_out.bias', 'learned_motion.linear_out.weight',
+              'learned_motion.linear_out.bias', 'phase_rbf.log_sigmas']
+    return names, [g.views[n] for n in names]
+
+
+def test_reference_optimizer_state_lands_in_the_flat_buffers():
+    """opt_sd[1] of the reference-written checkpoint -> FusedAdam.load_state_dict -> every exp_avg / exp_avg_sq sits at
+    the engine's offset of that tensor (row by row for the padded first-layer weight), pads stay zero, both step
+    counters are set; state_dict() gives the torch layout back bit for bit."""
+    args, _, _, _, _ = step_case(3)
+    ck = torch.load(os.path.join(GOLD, 'ref_ckpt_v3.pt'), weights_only=False)
+    sd = ck['opt_sd'][1]
+    h, in_dim, D = args.h_dim, args.phase_rbf_dim + args.instance_code_size, args.phase_rbf_dim
+    assert in_dim % 4 != 0   # the fixture exercises the padded row stride
+    g = _motion_group(h, in_dim, D)
+    names, params = _torch_order(g)
+    opt = FusedAdam(params, g, 1e-3, 1e-3)
+    opt.load_state_dict(sd)
+    assert int(g.step_dev) == 5 and int(g.step_lag_dev) == 2
+    used = torch.zeros_like(g.m, dtype=torch.bool)
+    for i, n in enumerate(names):
+        o, k = g.offsets[n]
+        ref_m, ref_v = sd['state'][i]['exp_avg'], sd['state'][i]['exp_avg_sq']
+        if n in g.padded:
+            rows, ld = g.padded[n].shape
+            mm, vv = g.m[o:o + k].view(rows, ld), g.v[o:o + k].view(rows, ld)
+            assert torch.equal(mm[:, :ref_m.shape[1]], ref_m) and torch.equal(vv[:, :ref_m.shape[1]], ref_v), n
+            assert float(mm[:, ref_m.shape[1]:].abs().sum()) == 0.0, n
+            used[o:o + k].view(rows, ld)[:, :ref_m.shape[1]] = True
+        else:
+            assert torch.equal(g.m[o:o + k], ref_m.reshape(-1)) and torch.equal(g.v[o:o + k], ref_v.reshape(-1)), n
+            used[o:o + k] = True
+    assert float(g.m[~used].abs().sum()) == 0.0 and float(g.v[~used].abs().sum()) == 0.0
+    back = opt.state_dict()
+    assert sorted(back['state']) == sorted(sd['state'])
+    for i in sd['state']:
+        assert float(back['state'][i]['step']) == float(sd['state'][i]['step']), i
+        assert torch.equal(back['state'][i]['exp_avg'], sd['state'][i]['exp_avg'])
+        assert torch.equal(back['state'][i]['exp_avg_sq'], sd['state'][i]['exp_avg_sq'])
+    assert back['param_groups'][0]['lr'] == sd['param_groups'][0]['lr']
+
+
+def test_fresh_optimizer_has_no_state_and_warmup_leaves_lagging_tensors_without():
+    g = _motion_group(48, 15, 12)
+    names, params = _torch_order(g)
+    opt = FusedAdam(params, g, 1e-3, 1e-3)
+    assert opt.state_dict()['state'] == {}
+    g.step_dev.fill_(3)   # three warm-up steps: linear_out.* (torch indices 8, 9) still have no state
+    assert sorted(opt.state_dict()['state']) == [0, 1, 2, 3, 4, 5, 6, 7, 10]
+
+
+def test_adam_segment_table():
+    """ranges() covers the buffer exactly once in maximal runs; one segment per step counter owns the increment;
+    skip_lag marks exactly the linear_out.* runs."""
+    from nemo_cvpr2023_b200._lib import ADAM_OWNS_STEP, ADAM_SKIP
+    g = _motion_group(1000, 105, 100)
+    rs = g.ranges()
+    assert [r[2] for r in rs] == [False, True, False, True, False]
+    assert rs[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(rs, rs[1:])) and rs[-1][0] + rs[-1][1] == g.p.numel()
+    assert all(r[0] % 4 == 0 for r in rs)
+    assert rs[1][:2] == g.offsets['learned_motion.linear_out.weight'] and rs[3][0] == g.offsets['learned_motion.linear_out.bias'][0]
+    segs = g.segments(skip_lag=True)
+    assert [bool(s.flags & ADAM_SKIP) for s in segs] == [False, True, False, True, False]
+    assert [bool(s.flags & ADAM_OWNS_STEP) for s in segs] == [True, True, False, False, False]
+    assert sum(s.n for s in segs) == g.p.numel()
+    plain = fe.ParamGroup([('learned_cameras', (8, 9))], 'cpu', 0.1)
+    assert plain.ranges() == [(0, 72, False)] and plain.segments()[0].flags == ADAM_OWNS_STEP
