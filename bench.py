@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the NeMo per-iteration fitting hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 0..4] [--impl reference]
 
-A "step" is one NemoV2.step (motion MLP -> SMPL LBS -> reprojection loss, + VPoser and GMM priors,
-forward + backward + Adam, exactly what the reference's `step` does) on a batch of 4096 (view, frame)
-samples per GPU -- the batch shape of BASELINE.json configs[1] through the full step of configs[0].
-Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+A "step" is one `NemoV*.step` (motion MLP -> SMPL LBS -> reprojection loss, + VPoser and GMM priors, forward +
+backward + Adam, exactly what the reference's `step` does).  The default workload (the headline, `--config 1`) is a
+batch of 4096 (view, frame) samples per GPU -- the batch of BASELINE.json configs[1] through the full step of
+configs[0], weak scaling.  `--config 0 / 2 / 3 / 4` run the other BASELINE configurations (strong scaling: the views
+are cut over the ranks).  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
 """
 from __future__ import annotations
 
@@ -28,9 +29,25 @@ sys.path.insert(0, ROOT)
 from nemo_cvpr2023_b200 import assets  # noqa: E402
 
 METRIC = 'fit frames/s fwd+bwd (MLP->SMPL->reproj loss)'
-V_PER_GPU, F_FRAMES = 8, 512          # 4096 samples per GPU per step
-CPU_V, CPU_F = 8, 64                  # bounded CPU sample: configs[0], 512 samples per step
 STREAM_BYTES = 6890 * 3 * 4           # one per-vertex fp32 stream of one frame
+
+# BASELINE.json configs.  V views x F frames per action; `weak`: V is per GPU, else the views are cut over the ranks.
+CONFIGS = {
+    0: dict(tag='configs[0]', version=2, actions=1, V=8, F=64, h=1000, weak=False,
+            what='NeMo baseball-pitch fit: 1 action x 8 video instances x 64 frames'),
+    1: dict(tag='configs[1] batch through the configs[0] step', version=2, actions=1, V=8, F=512, h=1000, weak=True,
+            what='8 views x 512 frames = 4096 samples per GPU per step'),
+    2: dict(tag='configs[2]', version=2, actions=8, V=8, F=128, h=1000, weak=False,
+            what='NeMo-MoCap scale fit: 8 actions (8 parameter sets) x 8 instances x 128 frames, instances cut over the '
+                 'ranks, ONE all-reduce of the 8 x 9 MB shared gradients'),
+    3: dict(tag='configs[3]', version=4, actions=1, V=64, F=512, h=1024, weak=False,
+            what='large-batch fit: 64 instances x 512 frames = 32768 samples, motion MLP width 1024, per-instance '
+                 'trainable cameras (NemoV4)'),
+    4: dict(tag='configs[4]', version=3, actions=1, V=16, F=256, h=1000, weak=False,
+            over=dict(weight_3d_loss=1000.0, weight_instance_loss=0.1),
+            what='custom-video path: NemoV3, 16 instances x 256 frames full batch, 2D OpenPose + 3D pose losses, '
+                 'per-instance codes'),
+}
 
 
 def bench_args(**over):
@@ -38,6 +55,10 @@ def bench_args(**over):
              weight_vp_loss=10.0, weight_vp_z_loss=1.0, weight_gmm_loss=1.0, loss='mse_robust')
     d.update(over)
     return assets.default_args(**d)
+
+
+def config_args(c, n):
+    return bench_args(batch_size=n, h_dim=c['h'], **c.get('over', {}))
 
 
 def peaks():
@@ -101,108 +122,199 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(rows)}
 
 
+def workload_config(cfg_id, gpus):
+    c = CONFIGS[cfg_id]
+    per_gpu = c['actions'] * c['V'] * c['F'] if c['weak'] else c['actions'] * c['V'] * c['F'] // gpus
+    return {'workload': 'Nemo%s.step fwd+bwd+Adam (motion MLP h=%d, RBF 100, code 5 -> SMPL LBS 6890 verts / 24 joints / '
+                        '10 betas -> projection -> mse_robust 2D loss + VPoser v2v/KL + GMM prior): %s (%s)'
+                        % ('V%d' % c['version'], c['h'], c['what'], c['tag']),
+            'baseline_config': cfg_id, 'samples_per_gpu': per_gpu, 'global_batch': per_gpu * gpus,
+            'l2_policy': 'per-step working set (340 MB pose-offset streams + gradients at 4096 samples) exceeds the '
+                         '126 MB L2' if per_gpu >= 2048 else 'working set of this small configuration fits the L2; every '
+                         'step rewrites all of it',
+            'parallelism': 'dp%d over video instances (views); NCCL all-reduce of the shared MLP gradients, bucketed and '
+                           'overlapped with the backward' % gpus}
+
+
 # ------------------------------------------------------------------------------------------ CPU arms
-def make_oracle(V, F, seed=0):
-    from oracle import nemo_oracle as O
-    args = bench_args(batch_size=V * F)
+def cpu_problem(c):
+    """The step of configuration `c` on ONE GPU's share at --gpus 1 (weak configs: one GPU's batch)."""
+    V, F = c['V'], c['F']
+    V = max(1, min(V, 4096 // F))        # bounded sample: at most 4096 samples per CPU step (configs[3]: 8 of its 64 views)
+    args = config_args(c, V * F)
     params = assets.make_fit_params(args, V, seed=4)
     data = assets.make_fit_data(V, F, seed=1)
-    orc = O.FitOracle(args, O.to_torch(params), O.to_torch(assets.make_smpl_assets(0)),
-                      O.to_torch(assets.make_vposer_weights(2)), O.to_torch(assets.make_gmm(3)), O.to_torch(data),
-                      version=2).build_optimizers()
     vi = torch.arange(V).repeat_interleave(F)
     fi = torch.arange(F).repeat(V)
-    return orc, vi, fi
+    return args, params, data, vi, fi
 
 
-def time_cpu(steps, warmup):
-    """The reference's algorithm (oracle port, PyTorch CPU, all host threads) on the bounded sample."""
+def make_cpu_step(c):
+    """-> (callable running one step, kind).  kind "reference": the UNMODIFIED reference's `NemoV*.step` from
+    oracle/_ref (or /root/reference where mounted); kind "port": the oracle restatement, when no reference copy is
+    present."""
+    from oracle import ref_harness as rh
+    args, params, data, vi, fi = cpu_problem(c)
+    sm, vp, gmm = assets.make_smpl_assets(0), assets.make_vposer_weights(2), assets.make_gmm(3)
+    if rh.available():
+        try:
+            with contextlib.redirect_stdout(sys.stderr):
+                mods = rh.setup(sm)
+                m = rh.build_fit_model(mods, args, params, sm, vp, gmm, data, version=c['version'])
+
+            def step():
+                with contextlib.redirect_stdout(sys.stderr):
+                    return m.step(vi, fi)[0]
+            return step, 'reference'
+        except Exception as e:  # a broken copy must not take the bench down: say so and time the port
+            sys.stderr.write('reference import failed (%r); timing the oracle port\n' % (e,))
+    from oracle import nemo_oracle as O
+    orc = O.FitOracle(args, O.to_torch(params), O.to_torch(sm), O.to_torch(vp), O.to_torch(gmm), O.to_torch(data),
+                      version=c['version']).build_optimizers()
+    return (lambda: orc.step(vi, fi)[0]), 'port'
+
+
+def time_cpu(c, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
-    orc, vi, fi = make_oracle(CPU_V, CPU_F)
+    step, kind = make_cpu_step(c)
     for _ in range(warmup):
-        orc.step(vi, fi)
+        step()
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        orc.step(vi, fi)
+        step()
         ts.append(time.perf_counter() - t0)
     med = float(np.median(ts))
-    return CPU_V * CPU_F / med, med, torch.get_num_threads()
+    n = max(1, min(c['V'], 4096 // c['F'])) * c['F']
+    return n / med, med, torch.get_num_threads(), kind, n
+
+
+def cpu_sample_text(c, kind, n, warmup, steps, med):
+    who = ("the unmodified reference's Nemo%s.step (oracle/_ref, PyTorch CPU fp32)" % ('V%d' % c['version'])
+           if kind == 'reference' else 'oracle port of the reference step (PyTorch CPU fp32)')
+    return ('%s, all host threads, on %d views x %d frames = %d samples per step (one action model of the GPU arm\'s '
+            'configuration, h=%d, all priors + Adam); %d warm-up + %d timed steps, median %.0f ms'
+            % (who, n // c['F'], c['F'], n, c['h'], warmup, steps, med * 1e3))
 
 
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 2))
-    fps, med, cores = time_cpu(steps, warmup)
-    sample = ('oracle port of the reference step (PyTorch CPU fp32), NemoV2.step on %d views x %d frames = %d '
-              'samples per step, h=1000, all priors + Adam; %d warm-up + %d timed steps, median'
-              % (CPU_V, CPU_F, CPU_V * CPU_F, warmup, steps))
+    c = CONFIGS[a.config]
+    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
+    fps, med, cores, kind, n = time_cpu(c, steps, warmup)
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': a.gpus,
-            'steps': steps, 'warmup': warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(a.gpus),
-            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'steps': steps, 'warmup': warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True,
+            'scaling': 'weak' if c['weak'] else 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(a.config, a.gpus),
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                             'sample': cpu_sample_text(c, kind, n, warmup, steps, med)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
 
 
-def workload_config(gpus):
-    return {'workload': 'NemoV2.step fwd+bwd+Adam (motion MLP h=1000, RBF 100, code 5 -> SMPL LBS 6890 verts / 24 joints '
-                        '/ 10 betas -> projection -> mse_robust 2D loss + VPoser v2v/KL + GMM prior), %d views x %d frames '
-                        '= %d samples per GPU per step (configs[1] batch through the configs[0] step)'
-                        % (V_PER_GPU, F_FRAMES, V_PER_GPU * F_FRAMES),
-            'samples_per_gpu': V_PER_GPU * F_FRAMES, 'global_batch': V_PER_GPU * F_FRAMES * gpus,
-            'l2_policy': 'per-step working set (3 x 340 MB pose-offset streams + gradients) exceeds the 126 MB L2',
-            'parallelism': 'dp%d over video instances (views); NCCL allreduce of shared MLP gradients' % gpus}
-
-
 # ------------------------------------------------------------------------------------------ GPU arm
-def k7_roofline(dev, iters=10):
-    """Skinning kernel pair timed alone with CUDA events: forward (read pose offsets, write vertices) +
-    backward (read pose offsets, read dV, write d pose offsets) = 5 per-vertex streams per frame."""
+def _time_events(fn, iters):
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def k7_roofline(dev, N, iters=10):
+    """Skinning kernels timed alone with CUDA events on the current stream.
+    pair: forward (read pose offsets, write vertices) + backward (read pose offsets, read dV, write d pose offsets)
+          = 5 per-vertex streams per frame -- the figure SURVEY.md 8(d) defines.
+    in_step: the two variants the fit step launches -- fused L1 of two meshes (read 2 pose-offset streams, write sign
+          bits) + backward from the sign bits (read pose offsets, write d pose offsets) = 4 streams per frame."""
     from nemo_cvpr2023_b200 import functional as Fn
     from nemo_cvpr2023_b200._lib import lib
-    N = V_PER_GPU * F_FRAMES
     C = Fn.SMPLConstants(assets.make_smpl_assets(0), dev)
     g = torch.Generator(device=dev).manual_seed(0)
     A = torch.randn(N, 24, 12, device=dev, generator=g)
+    A2 = A + 0.01 * torch.randn(N, 24, 12, device=dev, generator=g)
     PO = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
+    PO2 = 0.01 * torch.randn(N, 3 * Fn.VP, device=dev, generator=g)
     dV = torch.randn(N, Fn.NV, 3, device=dev, generator=g)
     Vout = torch.empty(N, Fn.NV, 3, device=dev)
     dPO, dAs = torch.empty_like(PO), torch.empty(N, 24, 12, device=dev)
-
-    def fwd():
-        lib.skin_fwd(A, PO, C.vt, C.Wt, Vout, N)
-
-    def bwd():
-        lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAs, N)
-
+    signs = torch.zeros(N, 3, 2, Fn.VP // 32, dtype=torch.int32, device=dev)
+    l1 = torch.zeros(1, device=dev)
     out = {}
-    for name, fn in (('fwd', fwd), ('bwd', bwd)):
-        for _ in range(3):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        out[name] = e0.elapsed_time(e1) / iters * 1e-3
-    return N, out
+    out['fwd'] = _time_events(lambda: lib.skin_fwd(A, PO, C.vt, C.Wt, Vout, N), iters)
+    out['bwd'] = _time_events(lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, dV, None, 0.0, dPO, dAs, N), iters)
+    out['l1_fwd'] = _time_events(lambda: lib.skin_l1_fwd(A, PO, A2, PO2, C.vt, C.Wt, signs, l1, N), iters)
+    out['bwd_signs'] = _time_events(lambda: lib.skin_bwd(A, PO, C.vt, C.Wt, None, signs, 1e-6, dPO, dAs, N), iters)
+    return out
 
 
 def k7_traffic(n):
     """dram__bytes_read + dram__bytes_write of the K7 launch pair from the committed ncu --set full capture (None
-    when the capture was taken at another batch size)."""
+    when the capture was taken at another batch size); the capture's file and commit are named in the JSON."""
     p = os.path.join(ROOT, 'profiles', 'k7_traffic.json')
     if not os.path.exists(p):
-        return None
+        return None, None
     d = json.load(open(p))
-    return d['fwd_dram_bytes'] + d['bwd_dram_bytes'] if d.get('n') == n else None
+    if d.get('n') != n:
+        return None, None
+    return d['fwd_dram_bytes'] + d['bwd_dram_bytes'], d.get('source', 'profiles/k7_traffic.json')
+
+
+def count_kernels(fn):
+    """Every GPU kernel (this library's AND ATen's fills / copies / NCCL) one call of `fn` launches, from CUPTI."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if getattr(e, 'device_type', None) is not None
+                 and str(e.device_type).endswith('CUDA') and not e.name.lower().startswith(('memcpy', 'memset'))]
+        mem = [e.name for e in prof.events() if str(getattr(e, 'device_type', '')).endswith('CUDA')
+               and e.name.lower().startswith(('memcpy', 'memset'))]
+        lib_marks = ('at::', 'nccl', 'cub::', 'thrust::', 'c10::')
+        repo = [n for n in names if not any(mk in n for mk in lib_marks)]
+        return {'kernels': len(names), 'repo': len(repo), 'other': len(names) - len(repo), 'memops': len(mem)}
+    except Exception as e:  # CUPTI unavailable: the library's own count stands
+        return {'error': repr(e)[:120]}
+
+
+def parity_check(dev):
+    """The GPU step and the CPU oracle on the SAME batch (configs[0]: 8 x 64 = 512 samples, h = 1000): worst relative
+    error over the loss terms and worst per-tensor relative L2 error over every parameter gradient."""
+    from nemo_cvpr2023_b200.nemo import neural_motion_model as nmm
+    from nemo_cvpr2023_b200.nemo.multi_view_sequence import SyntheticMultiViewSequence
+    from oracle import nemo_oracle as O
+    c = CONFIGS[0]
+    args, params, data, vi, fi = cpu_problem(c)
+    orc = O.FitOracle(args, O.to_torch(params), O.to_torch(assets.make_smpl_assets(0)),
+                      O.to_torch(assets.make_vposer_weights(2)), O.to_torch(assets.make_gmm(3)), O.to_torch(data),
+                      version=2).build_optimizers()
+    ref, _ = orc.step(vi, fi)
+    m = nmm.NemoV2(args, SyntheticMultiViewSequence(data=data), dev, init_params=params)
+    ld, _ = m.step(vi, fi)
+    loss_err = max(abs(float(ld[k]) - ref[k]) / max(abs(ref[k]), 1e-30) for k in ld)
+    grads = m.engine.named_grads()
+    gerr, worst = 0.0, ''
+    for k, p in orc.p.items():
+        if p.grad is None or k == 'learned_betas' or float(p.grad.abs().max()) == 0.0:
+            continue
+        g, r = grads[k].detach().cpu().double().reshape(-1), p.grad.double().reshape(-1)
+        e = float((g - r).norm() / r.norm())
+        if e > gerr:
+            gerr, worst = e, k
+    return {'against': 'CPU oracle (oracle/nemo_oracle.py) on the same batch: configs[0], 512 samples, h=1000',
+            'max_rel_loss_err': loss_err, 'max_rel_l2_grad_err': gerr, 'worst_grad': worst,
+            'tolerance': {'loss': 1e-5, 'grad': 1e-4}, 'ok': bool(loss_err <= 1e-5 and gerr <= 1e-4)}
 
 
 def run_gpu(a):
@@ -226,24 +338,57 @@ def run_gpu(a):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    try:
+        _run_gpu(a, rank, local, world, dev)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+def _run_gpu(a, rank, local, world, dev):
+    from nemo_cvpr2023_b200 import dp
     from nemo_cvpr2023_b200._lib import lib
+    from nemo_cvpr2023_b200.multi_action import MultiActionFit
     from nemo_cvpr2023_b200.nemo import neural_motion_model as nmm
     from nemo_cvpr2023_b200.nemo.multi_view_sequence import SyntheticMultiViewSequence
 
-    N = V_PER_GPU * F_FRAMES
-    args = bench_args(batch_size=N)
-    params = assets.make_fit_params(args, V_PER_GPU, seed=4 + rank)
-    # shared (data-parallel) parameters start identical on every rank
-    shared = assets.make_fit_params(args, V_PER_GPU, seed=4)
-    for k in shared:
-        if k.startswith('learned_motion.') or k.startswith('phase_rbf.'):
-            params[k] = shared[k]
-    model = nmm.NemoV2(args, SyntheticMultiViewSequence(V_PER_GPU, F_FRAMES, seed=1 + rank), dev, init_params=params)
+    c = CONFIGS[a.config]
+    cls = {2: nmm.NemoV2, 3: nmm.NemoV3, 4: nmm.NemoV4}[c['version']]
+    F_total = c['F']
+    if c['weak']:
+        plan = dict(views=list(range(c['V'])), frame_lo=0, frame_hi=F_total, reduce_all=False)
+        V_glob = c['V']
+    else:
+        plan = dp.shard_plan(c['V'], F_total, world, rank)
+        V_glob = c['V']
+    Vl, Fl = len(plan['views']), plan['frame_hi'] - plan['frame_lo']
+    N = Vl * Fl                                   # samples per action model per step on this rank
+    args = config_args(c, N)
+    models = []
+    for act in range(c['actions']):
+        # shared (data-parallel) parameters start identical on every rank; per-view ones belong to the view
+        full_p = assets.make_fit_params(args, V_glob, seed=4 + 100 * act + (rank if c['weak'] else 0))
+        shared = assets.make_fit_params(args, V_glob, seed=4 + 100 * act)
+        for k in shared:
+            if dp.is_shared(k):
+                full_p[k] = shared[k]
+        full_d = assets.make_fit_data(V_glob, F_total, seed=1 + 100 * act + (rank if c['weak'] else 0))
+        p = dp.shard_fit_params(full_p, plan['views'])
+        d = dp.shard_fit_data_frames(full_d, plan['views'], plan['frame_lo'], plan['frame_hi'])
+        m = cls(args, SyntheticMultiViewSequence(data=d), dev, init_params=p)
+        if Fl != F_total:
+            m.engine.set_frame_window(plan['frame_lo'], F_total)
+        models.append(m)
+    multi = MultiActionFit(models, dev) if c['actions'] > 1 else None
     if world > 1:
-        model.engine.enable_data_parallel(world)
-    vi_h = torch.arange(V_PER_GPU).repeat_interleave(F_FRAMES).pin_memory()
-    fi_h = torch.arange(F_FRAMES).repeat(V_PER_GPU).pin_memory()
+        if multi:
+            multi.enable_data_parallel(world, reduce_all=plan['reduce_all'])
+        else:
+            models[0].engine.enable_data_parallel(world, reduce_all=plan['reduce_all'])
+    vi_h = torch.arange(Vl).repeat_interleave(Fl).pin_memory()
+    fi_h = torch.arange(Fl).repeat(Vl).pin_memory()
     vi_d, fi_d = vi_h.to(dev), fi_h.to(dev)
+    A = c['actions']
 
     def barrier():
         if world > 1:
@@ -263,18 +408,29 @@ def run_gpu(a):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t)
 
+    model = models[0]
     eng = model.engine
+    train = c['version'] >= 3
 
-    def dev_step():      # inputs resident in HBM, no host read-back
-        eng.training = False
-        eng.forward_backward(vi_d, fi_d, update=True, mode='step')
-        eng.optimizer_step()
+    if multi:
+        def dev_step():
+            multi.forward_backward([vi_d] * A, [fi_d] * A, update=True)
+            multi.optimizer_step()
 
-    def e2e_step():      # the public call: pinned host indices in, loss dict out
-        model.step(vi_h, fi_h)
+        def e2e_step():
+            multi.step([vi_h] * A, [fi_h] * A)
+    else:
+        def dev_step():      # inputs resident in HBM, no host read-back
+            eng.training = train
+            eng.forward_backward(vi_d, fi_d, update=True, mode='step')
+            eng.optimizer_step()
+
+        def e2e_step():      # the public call: pinned host indices in, loss dict out
+            model.step(vi_h, fi_h)
 
     cs = ClockSampler(local).start()
-    for _ in range(max(3, a.warmup)):
+    warm = max(3, a.warmup)
+    for _ in range(warm):
         dev_step()
     with cs.window():
         l0 = lib.launches
@@ -284,38 +440,50 @@ def run_gpu(a):
         e2e_step()
     with cs.window():
         t_e2e = timed(e2e_step, a.steps)
+    kernels = count_kernels(dev_step)     # every rank: the step holds a collective
     if rank != 0:
         cs.stop()
         return
-    total = N * world
+    total = A * N * world
     value = total * a.steps / t_dev
     e2e_val = total * a.steps / t_e2e
     peak, peak_src = peaks()
+    nK7 = 4096
     with cs.window():
-        nK7, tk = k7_roofline(dev)
+        tk = k7_roofline(dev, nK7)
     cs.stop()
     clocks = cs.summary()
     alg = 5 * STREAM_BYTES * nK7
     achieved = alg / (tk['fwd'] + tk['bwd']) / 1e9
-    cpu_fps, cpu_med, cores = time_cpu(3, 1)
+    alg_in = 4 * STREAM_BYTES * nK7
+    in_step = alg_in / (tk['l1_fwd'] + tk['bwd_signs']) / 1e9
+    traffic, traffic_src = k7_traffic(nK7)
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(3, a.warmup),
-        'ms_per_step': t_dev / a.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world), 'clocks': clocks,
-        'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': int(2 * N * 8),
-                'd2h_bytes_per_step': 9 * 4, 'ms_per_step': t_e2e / a.steps * 1e3},
-        'gpu_launches': int(launches),
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': a.steps, 'warmup': warm,
+        'ms_per_step': t_dev / a.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak' if c['weak'] else 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(a.config, world),
+        'clocks': clocks,
+        'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': int(A * 2 * N * 8),
+                'd2h_bytes_per_step': A * 9 * 4, 'ms_per_step': t_e2e / a.steps * 1e3},
+        'gpu_launches': int(kernels.get('kernels', launches)),
+        'gpu_launches_detail': dict(kernels, repo_c_abi_count=int(launches)),
         'roofline': {'bound': 'hbm', 'kernel': 'k_skin_tc_fwd<0> + k_skin_tc_bwd<dV> (K7, vertices written, dV read: 5 streams/frame)',
                      'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': k7_traffic(nK7),
-                     'algorithmic_bytes_per_launch_pair': alg, 'fwd_ms': tk['fwd'] * 1e3, 'bwd_ms': tk['bwd'] * 1e3,
+                     'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                     'algorithmic_bytes_per_launch_pair': alg, 'frames_per_launch': nK7,
+                     'fwd_ms': tk['fwd'] * 1e3, 'bwd_ms': tk['bwd'] * 1e3,
                      'fwd_frac': 2 * STREAM_BYTES * nK7 / tk['fwd'] / 1e9 / peak,
-                     'bwd_frac': 3 * STREAM_BYTES * nK7 / tk['bwd'] / 1e9 / peak},
-        'cpu_baseline': {'value': cpu_fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                         'sample': 'oracle port of NemoV2.step (PyTorch CPU fp32, all host threads) on %d views x %d '
-                                   'frames = %d samples per step, 1 warm-up + 3 timed steps, median %.0f ms'
-                                   % (CPU_V, CPU_F, CPU_V * CPU_F, cpu_med * 1e3)},
+                     'bwd_frac': 3 * STREAM_BYTES * nK7 / tk['bwd'] / 1e9 / peak,
+                     'in_step': {'kernel': 'k_skin_tc_fwd<1> (fused L1 of two meshes) + k_skin_tc_bwd<signs>: the variants '
+                                           'the timed step launches, 4 streams/frame',
+                                 'achieved': in_step, 'frac': in_step / peak, 'algorithmic_bytes_per_launch_pair': alg_in,
+                                 'l1_fwd_ms': tk['l1_fwd'] * 1e3, 'bwd_signs_ms': tk['bwd_signs'] * 1e3}},
     }
+    if world == 1:
+        line['parity'] = parity_check(dev)
+        cpu_fps, cpu_med, cores, kind, n_cpu = time_cpu(c, 3, 1)
+        line['cpu_baseline'] = {'value': cpu_fps, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                                'sample': cpu_sample_text(c, kind, n_cpu, 1, 3, cpu_med)}
     print(json.dumps(line))
 
 
@@ -324,6 +492,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--config', type=int, default=1, choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     a = ap.parse_args()
     if a.impl == 'reference':

@@ -30,6 +30,26 @@ def shard_views(num_views: int, world: int, rank: int) -> list:
     return list(range(rank * per, (rank + 1) * per))
 
 
+def shard_plan(num_views: int, num_frames: int, world: int, rank: int) -> dict:
+    """Which (views, frame window) `rank` fits.  Views are split first; with more ranks than views
+    (V < G) every view's frames are cut into world / V equal windows, and the view's camera / phase / instance-code
+    gradients have to be summed over the ranks that share it (`reduce_all`).  Equal shards only."""
+    if num_views % world == 0:
+        return dict(views=shard_views(num_views, world, rank), frame_lo=0, frame_hi=num_frames, reduce_all=False)
+    if world % num_views == 0 and num_frames % (world // num_views) == 0:
+        per_view = world // num_views
+        n = num_frames // per_view
+        k = rank % per_view
+        return dict(views=[rank // per_view], frame_lo=k * n, frame_hi=(k + 1) * n, reduce_all=True)
+    raise ValueError('cannot cut %d views x %d frames into %d equal shards' % (num_views, num_frames, world))
+
+
+def shard_fit_data_frames(data: dict, views: list, frame_lo: int, frame_hi: int) -> dict:
+    """`shard_fit_data` + a frame window on every (V,F,...) entry."""
+    out = shard_fit_data(data, views)
+    return {k: (v[:, frame_lo:frame_hi] if hasattr(v, 'shape') and len(v.shape) >= 2 else v) for k, v in out.items()}
+
+
 def is_shared(name: str) -> bool:
     return name.startswith(SHARED_PREFIXES)
 

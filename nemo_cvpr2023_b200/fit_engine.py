@@ -243,13 +243,64 @@ class FitEngine:
         self.map25 = torch.tensor(m25, dtype=torch.int32, device=self.dev)
         self._ws = {}
         self.training = False
-        self.world, self.loss_scale = 1, 1.0
+        self.world, self.loss_scale, self.dp_defer = 1, 1.0, False
 
-    def enable_data_parallel(self, world_size):
+    def enable_data_parallel(self, world_size, group=None, reduce_all=False, overlap=True):
         """Shard by video instance: this rank owns its views' cameras, instance codes and
-        phase networks; the shared motion MLP + RBF gradients are summed over ranks with one NCCL allreduce per
-        step.  The global loss is the mean of the ranks' losses, so local gradients are scaled by 1/world."""
+        phase networks; the shared motion MLP + RBF gradients are summed over ranks.  The global loss is the mean of
+        the ranks' losses (equal shards), so local gradients are scaled by 1/world.
+
+        overlap: the flat gradient is reduced in four buckets (head, layer 4, layer 2, layer 0 + RBF widths) on a
+        communication stream as soon as the backward has produced each of them, so only the last, small bucket is
+        exposed; the compute stream joins before Adam.  reduce_all: a view's frames are split over ranks (more GPUs
+        than views), so its camera / phase / instance gradients are summed as well (one more small all-reduce)."""
         self.world, self.loss_scale = int(world_size), 1.0 / int(world_size)
+        self.dp_group, self.dp_reduce_all, self.dp_overlap = group, bool(reduce_all), bool(overlap)
+        self._dp_handles, self._comm = [], None
+        off = self.g_motion.offsets
+        o4, o2 = off['learned_motion.net.net.4.weight'][0], off['learned_motion.net.net.2.weight'][0]
+        oh = off['learned_motion.rot_out.weight'][0]
+        ot = off['phase_rbf.log_sigmas'][0] if self.D > 0 else self.g_motion.g.numel()
+        self._dp_buckets = dict(head=(oh, ot), l4=(o4, oh), l2=(o2, o4), l0=(0, o2), tail=(ot, self.g_motion.g.numel()))
+
+    def set_frame_window(self, frame_lo, total_frames):
+        """This engine holds frames [frame_lo, frame_lo + F) of sequences that are `total_frames` long (data-parallel
+        frame split): the raw phase of a frame is its position in the WHOLE sequence (:2978-2984)."""
+        self.phase_table = torch.linspace(0, 1, int(total_frames), device=self.dev)[int(frame_lo):int(frame_lo) + self.F].contiguous()
+
+    def _dp_bucket(self, name):
+        """all-reduce one finished range of the shared gradient on the communication stream"""
+        if self.world <= 1 or not self.dp_overlap:
+            return
+        import torch.distributed as dist
+        lo, hi = self._dp_buckets[name]
+        if hi <= lo:
+            return
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.dev)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            self._dp_handles.append(dist.all_reduce(self.g_motion.g[lo:hi], group=self.dp_group, async_op=True))
+
+    def _dp_finish(self):
+        import torch.distributed as dist
+        if self.dp_overlap:
+            self._dp_bucket('tail')
+        else:
+            dist.all_reduce(self.g_motion.g, group=self.dp_group)
+        if self.dp_reduce_all:
+            small = [g.g for g in (self.g_cam, self.g_phase, self.g_inst) if g is not None]
+            flat = torch.cat(small)
+            dist.all_reduce(flat, group=self.dp_group)
+            o = 0
+            for g in small:
+                g.copy_(flat[o:o + g.numel()])
+                o += g.numel()
+        for h in self._dp_handles:
+            h.wait()          # the compute stream waits for the collective; the host does not block
+        self._dp_handles = []
 
     # ------------------------------------------------------------------ parameters
     def named_params(self):
@@ -523,11 +574,11 @@ class FitEngine:
                 w['dY'][:N, 144:147].copy_(w['dtr'])
                 w['dY'][N, 144:147].copy_(w['dtr'].sum(0).neg_())
             self._motion_backward(w, N, vi)
-            if self.world > 1:
-                torch.distributed.all_reduce(self.g_motion.g)
             if w_inst:
                 self.g_inst.gviews['learned_instance_code'].add_(
                     self.g_inst.views['learned_instance_code'], alpha=ls * 2.0 * w_inst / (self.V * self.Cc))
+            if self.world > 1 and not self.dp_defer:
+                self._dp_finish()
         elif need_2d:
             lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox, self.focal, cx,
                             cy, 100.0, mode_id, red, w['view_acc'], 0.0, w['dj25'], None, acc[4:5], N, 25, self.V, self.F)
@@ -567,16 +618,20 @@ class FitEngine:
         # rows above it); keep it an exact 0 like the reference instead of summation-order noise that Adam
         # would amplify into lr-sized steps
         self.gbhead[144:147].zero_()
+        self._dp_bucket('head')
         gemm(dY, self.Whead, w['dHa'], Np, h, 147, LDY, h, h, gate=w['H3'], ldg=h)
         gemm(w['dHa'], w['H2'], gW(4), h, h, Np, h, h, h, transA=True)
         lib.colsum(w['dHa'], gb(4), Np, h, h, 0)
+        self._dp_bucket('l4')
         gemm(w['dHa'], W(4), w['dHb'], Np, h, h, h, h, h, gate=w['H2'], ldg=h)
         gemm(w['dHb'], w['H1'], gW(2), h, h, Np, h, h, h, transA=True)
         lib.colsum(w['dHb'], gb(2), Np, h, h, 0)
+        self._dp_bucket('l2')
         gemm(w['dHb'], W(2), w['dHa'], Np, h, h, h, h, h, gate=w['H1'], ldg=h)
         gemm(w['dHa'], w['X'], self.g_motion.gpadded['learned_motion.net.net.0.weight'], h, ind, Np, h, self.ldx,
              self.ldx, transA=True)
         lib.colsum(w['dHa'], gb(0), Np, h, h, 0)
+        self._dp_bucket('l0')
         gemm(w['dHa'], self.g_motion.padded['learned_motion.net.net.0.weight'], w['dX'], Np, ind, h, h, self.ldx,
              self.ldx)
         gp, gg = self.g_phase.views, self.g_phase.gviews
@@ -599,7 +654,16 @@ class FitEngine:
     # ------------------------------------------------------------------ read-backs
     def loss_dict(self, w, norm):
         """One packed device->host copy of the step's scalars (the reference does 5-7, :3564-3584)."""
-        host = torch.cat([w['acc'], w['total']]).cpu().numpy().astype(np.float64)
+        vec = torch.cat([w['acc'], w['total']])
+        if self.world > 1:
+            # global losses (the mean of the ranks' equal shards): what the reference would print on one GPU and what
+            # the plateau schedulers must see so that every rank takes the same decision (SURVEY.md 8(e))
+            torch.distributed.all_reduce(vec, group=self.dp_group)
+            vec /= self.world
+        return self.loss_dict_from_host(vec.cpu().numpy().astype(np.float64), norm)
+
+    @staticmethod
+    def loss_dict_from_host(host, norm):
         n = norm
         d = dict(kp_loss=host[4], vp_recon_loss=host[0] * n[0], vp_kl_loss=host[1] * n[1], gmm_loss=host[3] * n[3],
                  loss_3d=host[2], instance_loss=host[5], total_loss=host[8])

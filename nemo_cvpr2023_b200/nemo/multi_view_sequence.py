@@ -39,47 +39,55 @@ MultiViewSequence = SyntheticMultiViewSequence
 # `<name>.op/%06d_keypoints.json` = OpenPose BODY_25, `<name>.vibe/vibe_output.pkl`, optional `<name>.cam.pickle`),
 # same frame sampling (`tidx = floor(phase * n_seq_frames)`), same person selection, same output layout
 # (`sequences[v][key][f]`).  Host-side file IO only; nothing here touches the GPU.
+_PASS_THROUGH = ('betas', 'frame_ids')   # per-track entries the reference keeps at track length (:33-35)
+
+
+def _densify(track, n_frames):
+    """One VIBE track -> arrays indexed by video frame.  Every per-frame array of the track is scattered to its
+    `frame_ids` rows of a zero float32 array of `n_frames` rows, and `mask` marks the frames the person was tracked on
+    (semantics of prepare_person_dict, nemo/multi_view_sequence.py:30-48; `None` entries are dropped)."""
+    ids = np.asarray(track['frame_ids'], dtype=np.int64)
+    present = np.zeros(n_frames, dtype=np.float32)
+    present[ids] = 1.0
+    dense = {k: track[k] for k in _PASS_THROUGH if k in track}
+    for name, values in track.items():
+        if name in _PASS_THROUGH or values is None:
+            continue
+        values = np.asarray(values)
+        out = np.zeros((n_frames,) + values.shape[1:], dtype=np.float32)
+        out[ids] = values
+        dense[name] = out
+    dense['mask'] = present
+    return dense
+
+
 def prepare_person_dict(person_output, max_frames):
-    """:30-48: scatter a VIBE track onto all `max_frames` frames (zeros where the person is absent) + `mask`."""
-    new_output = {}
-    for key in person_output:
-        if key in ['betas', 'frame_ids']:
-            new_output[key] = person_output[key]
-            continue
-        old_values = person_output[key]
-        if old_values is None:
-            continue
-        shape = list(old_values.shape)
-        shape[0] = max_frames
-        new_values = np.zeros(shape).astype('float32')
-        new_values[person_output['frame_ids']] = old_values
-        new_output[key] = new_values
-    mask = np.zeros((max_frames)).astype('float32')
-    mask[person_output['frame_ids']] = 1
-    new_output['mask'] = mask
-    return new_output
+    return _densify(person_output, max_frames)
 
 
 def prepare_vibe_dict(vibe_output, max_frames):
-    """:51-55"""
-    return {pid: prepare_person_dict(vibe_output[pid], max_frames) for pid in vibe_output}
+    """:51-55: every track of a `vibe_output.pkl` densified."""
+    return {pid: _densify(track, max_frames) for pid, track in vibe_output.items()}
 
 
 def select_person_at_center(vibe_output, img_size, max_frames, all_gt_2d):
-    """:58-89: the track whose mean 2-D joint centre is closest (masked mean distance) to the labels' centre."""
-    if vibe_output == {}:
+    """:58-89: the track that follows the 2-D labels most closely.  Score of a track = distance between the mean of
+    its first 15 projected joints and the mean of the labels, averaged over the frames the track is present on; the
+    lowest score wins, ties go to the first track (`img_size` / `max_frames` are unused there as well)."""
+    if not vibe_output:
         return None
-    ret_key, best_dist = 0, np.inf
-    for key in vibe_output:
-        person_output = vibe_output[key]
-        joints2d = person_output['joints2d_img_coord' if 'joints2d_img_coord' in person_output else 'smpl_joints2d']
-        centers = joints2d[:, :15].mean(1)
-        gt_centers = all_gt_2d.mean(1)
-        mask = person_output['mask']
-        cur_dist = (np.sqrt(((np.array(centers) - np.array(gt_centers)) ** 2).sum(-1)) * mask).sum() / mask.sum()
-        if cur_dist < best_dist:
-            ret_key, best_dist = key, cur_dist
-    return vibe_output[ret_key]
+    keys = list(vibe_output)
+    target = np.asarray(all_gt_2d).mean(1)                                     # (T, 2)
+    scores = np.empty(len(keys))
+    for i, k in enumerate(keys):
+        tr = vibe_output[k]
+        j2d = np.asarray(tr['joints2d_img_coord'] if 'joints2d_img_coord' in tr else tr['smpl_joints2d'])
+        off = np.linalg.norm(j2d[:, :15].mean(1) - target, axis=-1)            # (T,)
+        scores[i] = (off * tr['mask']).sum() / tr['mask'].sum()
+    # the reference starts from `best = inf` with a strict `<`: a NaN score never wins
+    scores = np.where(np.isnan(scores), np.inf, scores)
+    best = int(np.argmin(scores))
+    return vibe_output[keys[best]] if np.isfinite(scores[best]) else vibe_output.get(0, vibe_output[keys[0]])
 
 
 def _read_openpose(op_file, scale2=False):

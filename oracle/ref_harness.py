@@ -27,7 +27,10 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-REF = '/root/reference'
+# the mounted reference in the build container; on the GPU box the byte-identical copy of the path's files that
+# `python -m oracle.build_ref` made (git-ignored, shipped with the snapshot)
+_LOCAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+REF = '/root/reference' if os.path.isdir('/root/reference/nemo') else _LOCAL
 _state = {}
 
 

@@ -90,3 +90,63 @@ def test_shard_views_rejects_uneven_split():
     with pytest.raises(ValueError):
         dp.shard_views(5, 2, 0)
     assert dp.shard_views(8, 4, 3) == [6, 7]
+
+
+def test_shard_plan_views_then_frames():
+    """views first; with more ranks than views every view's frames are cut into equal windows (V < G)"""
+    p = dp.shard_plan(8, 64, 4, 1)
+    assert p == dict(views=[2, 3], frame_lo=0, frame_hi=64, reduce_all=False)
+    plans = [dp.shard_plan(2, 64, 8, r) for r in range(8)]
+    assert [q['views'] for q in plans] == [[0]] * 4 + [[1]] * 4
+    assert [(q['frame_lo'], q['frame_hi']) for q in plans[:4]] == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    assert all(q['reduce_all'] for q in plans)
+    cover = np.zeros((2, 64), int)
+    for q in plans:
+        cover[q['views'][0], q['frame_lo']:q['frame_hi']] += 1
+    assert (cover == 1).all()
+    with pytest.raises(ValueError):
+        dp.shard_plan(3, 64, 8, 0)
+    d = dp.shard_fit_data_frames(assets.make_fit_data(2, 64, seed=1), [1], 16, 32)
+    assert d['points2d_gt_all'].shape == (1, 16, 25, 3) and d['gt_bbox_size'].shape == (1, 16) and d['IMG_D0'] == 1080
+
+
+def _frame_split_worker(rank, world, port, out_path):
+    """V = 1 view cut into two frame windows: every gradient (shared AND the view's own) is summed over the ranks and
+    must equal the single-process gradient; the raw phase of a frame is its position in the WHOLE sequence."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    args = _args()
+    full_p, full_d = assets.make_fit_params(args, 1, seed=7), assets.make_fit_data(1, FR * 2, seed=1)
+    plan = dp.shard_plan(1, FR * 2, world, rank)
+    assert plan['reduce_all']
+    orc = _oracle(dp.shard_fit_params(full_p, plan['views']),
+                  dp.shard_fit_data_frames(full_d, plan['views'], plan['frame_lo'], plan['frame_hi']), args)
+    n = plan['frame_hi'] - plan['frame_lo']
+    vi, fi = torch.zeros(n, dtype=torch.long), torch.arange(n)
+    orc.raw_phase = lambda f: torch.linspace(0, 1, FR * 2)[f + plan['frame_lo']]
+    out, _ = orc.losses(vi, fi)
+    (out['total_loss'] / world).backward()
+    grads = [t.grad for t in orc.p.values() if t.grad is not None]
+    dp.allreduce_shared_(grads)
+    np.savez(out_path % rank, **{k: t.grad.numpy() for k, t in orc.p.items() if t.grad is not None})
+    dist.destroy_process_group()
+
+
+def test_frame_split_reproduces_single_process_gradients(tmp_path):
+    world = 2
+    out_path = str(tmp_path / 'fs%d.npz')
+    mp.spawn(_frame_split_worker, args=(world, 29100 + (os.getpid() % 300), out_path), nprocs=world, join=True)
+    args = _args()
+    orc = _oracle(assets.make_fit_params(args, 1, seed=7), assets.make_fit_data(1, FR * 2, seed=1), args)
+    vi, fi = torch.zeros(FR * 2, dtype=torch.long), torch.arange(FR * 2)
+    out, _ = orc.losses(vi, fi)
+    out['total_loss'].backward()
+    for r in range(world):
+        res = dict(np.load(out_path % r))
+        for k, t in orc.p.items():
+            if t.grad is None or k == 'learned_betas':
+                continue
+            g = t.grad.numpy()
+            assert np.linalg.norm(res[k] - g) <= 1e-4 * max(np.linalg.norm(g), 1e-30) + 1e-12, k
