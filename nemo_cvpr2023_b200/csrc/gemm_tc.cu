@@ -15,8 +15,12 @@
 //                                by shared-memory descriptor) into a TMEM partial (2 x 128 columns, double buffered)
 //   warps 8-15   accumulate +    tcgen05.ld the partial every `flush` k-blocks and add it into fp32 registers
 //                epilogue        (round-to-nearest; the tensor core accumulates with truncation, ~K/8*3*2^-24
-//                                relative on long chains), 64 columns per warp; then bias / activation / gate /
-//                                accumulate and 16-byte vector stores straight from registers (atomics under split-K)
+//                                relative on long chains), 64 columns per warp; then bias / activation / gate and the
+//                                tile leaves through a swizzled shared-memory box and ONE TMA store per 32 x 32 block
+//                                (TMA reduce-add for C += and for split-K: the sum happens at the L2).  A per-thread
+//                                row store (each lane its own row: 32 cache lines per instruction) cost ~150 cycles
+//                                per instruction in the LSU -- 14k cycles per tile against 37k of MMAs at K = 1000
+//                                (tools/gemm_probe.py) -- and stalled the MMA warp behind the undrained partial
 // A may be K-major (128-byte swizzle) or MN-major (128-byte swizzle with 32-byte atoms; un-transposed by the
 // converters), B K-major or MN-major (the only MN-major layout tf32 operands support), so NN / NT / TN / TT all
 // run without a transpose pass.  M, N, K tails are handled by TMA zero fill and predicated stores.
@@ -39,11 +43,14 @@ constexpr int BCONV_THREADS = 64, ACONV_THREADS = 128, ACC_THREADS = 256;
 constexpr int NC = BN / 2;                         // accumulator columns per epilogue thread
 constexpr int A_BYTES = BM * BK * 4;               // 16 KB
 constexpr int B_BYTES = BN * BK * 4;               // 16 KB
-constexpr int RAW_STAGES = 4, LO_STAGES = 2;
-constexpr int RAW_BYTES = A_BYTES + B_BYTES;       // [A raw][B raw = hi operand]
-constexpr int STAGING_BYTES = 8 * 32 * 33 * 4;     // one padded 32x32 transpose tile per epilogue warp
-constexpr int OFF_LO = RAW_STAGES * RAW_BYTES;     // B lo ring
-constexpr int OFF_STAGING = OFF_LO + LO_STAGES * B_BYTES;
+constexpr int RAW_STAGES = 4;
+constexpr int RAW_BYTES = A_BYTES + B_BYTES;       // [A raw][B raw = hi operand], the bytes TMA delivers per stage
+constexpr int STAGE_BYTES = RAW_BYTES + B_BYTES;   // + [B lo]: written by the converters, as deep as the raw ring (a
+                                                   // 2-deep lo ring made MMA(k) wait for convert(k) which waited for
+                                                   // MMA(k-2): period (convert + MMA) / 2 per k-block, measured)
+constexpr int STAGING_BYTES = 8 * 32 * 33 * 4;     // per epilogue warp: one 32 x 32 box (4 KB, 128-byte swizzle) for the TMA
+                                                   // store, or a padded 32 x 33 transpose tile on the unaligned path
+constexpr int OFF_STAGING = RAW_STAGES * STAGE_BYTES;
 constexpr int OFF_BARS = OFF_STAGING + STAGING_BYTES;
 constexpr int TMEM_COLS = 512;                     // partials 2 x 128 | A stages 4 x (32 hi + 32 lo)
 constexpr int TMEM_A = 2 * BN;
@@ -61,65 +68,11 @@ struct GemmParams {
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// Epilogue straight from the accumulator registers: this thread owns row m, NC consecutive columns from ncol0.
-// 16-byte vector stores (each lane its own row; consecutive instructions complete the 32-byte sectors in L2).
-// OUT 0 store, 1 read-add-store, 2 atomics (split-K).
-template <int OUT, bool HAS_GATE>
-__device__ __forceinline__ void epilogue_row(const GemmParams& p, const float (&acc)[NC], size_t m, int ncol0, bool add_bias) {
-  float* crow = p.C + m * p.ldc + ncol0;
-  const float* grow = HAS_GATE ? p.gate + m * p.ldg + ncol0 : nullptr;
-#pragma unroll
-  for (int c4 = 0; c4 < NC / 4; ++c4) {
-    const int n = ncol0 + 4 * c4;
-    if (n >= p.N) break;  // uniform
-    float x[4] = {acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]};
-    const bool full = n + 3 < p.N;
-    if (add_bias) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) x[k] += (n + k < p.N) ? __ldg(p.bias + n + k) : 0.f;
-    }
-    if (p.act == 1) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) x[k] = fmaxf(x[k], 0.f);
-    } else if (p.act == 2) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) x[k] = x[k] > 0.f ? x[k] : 0.01f * x[k];
-    }
-    if (full) {
-      if (HAS_GATE) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(grow + 4 * c4));
-        x[0] *= g.x > 0.f ? 1.f : p.gslope; x[1] *= g.y > 0.f ? 1.f : p.gslope;
-        x[2] *= g.z > 0.f ? 1.f : p.gslope; x[3] *= g.w > 0.f ? 1.f : p.gslope;
-      }
-      float4* cp = reinterpret_cast<float4*>(crow + 4 * c4);
-      if (OUT == 2) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) atomicAdd(crow + 4 * c4 + k, x[k]);
-      } else if (OUT == 1) {
-        const float4 o = *cp;
-        *cp = make_float4(o.x + x[0], o.y + x[1], o.z + x[2], o.w + x[3]);
-      } else {
-        *cp = make_float4(x[0], x[1], x[2], x[3]);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (n + k < p.N) {
-          float y = x[k];
-          if (HAS_GATE) y *= __ldg(grow + 4 * c4 + k) > 0.f ? 1.f : p.gslope;
-          float* cp = crow + 4 * c4 + k;
-          if (OUT == 2) atomicAdd(cp, y);
-          else if (OUT == 1) *cp += y;
-          else *cp = y;
-        }
-      }
-    }
-  }
-}
-
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB,
+                                                            const __grid_constant__ CUtensorMap tmC,
+                                                            const __grid_constant__ CUtensorMap tmG,
                                                             const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -127,10 +80,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   auto full = [&](int s) { return bars + 8u * s; };                          // TMA landed            (tx)
   auto conv = [&](int s) { return bars + 8u * (RAW_STAGES + s); };           // A in TMEM, B lo ready (192)
   auto empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };      // MMAs done with stage  (commit)
-  auto loempty = [&](int l) { return bars + 8u * (3 * RAW_STAGES + l); };    // MMAs done with B lo   (commit)
   auto pfull = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 2 + b); };  // partial complete      (commit)
   auto pempty = [&](int b) { return bars + 8u * (3 * RAW_STAGES + 4 + b); }; // partial drained       (256)
   const uint32_t tmem_slot = bars + 8u * (3 * RAW_STAGES + 6);
+  auto gbar = [&](int w) { return bars + 8u * (3 * RAW_STAGES + 8 + w); };   // gate box of epilogue warp w landed (tx)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -141,8 +94,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       mbar_init(conv(s), ACONV_THREADS + BCONV_THREADS);
       mbar_init(empty(s), 1);
     }
+    for (int w = 0; w < 8; ++w) mbar_init(gbar(w), 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(loempty(b), 1);
       mbar_init(pfull(b), 1);
       mbar_init(pempty(b), ACC_THREADS);
     }
@@ -174,7 +127,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
           const int s = it % RAW_STAGES;
           mbar_wait(empty(s), ((it / RAW_STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(full(s), RAW_BYTES);
-          const uint32_t sa = sbase + s * RAW_BYTES, sb = sa + A_BYTES;
+          const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
           if (!A_MN) {
             tma_load_2d(sa, &tmA, full(s), kb * BK, mb * BM);
           } else {
@@ -205,11 +158,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
           const uint32_t d = tmem_base + pb * BN;
           const int kce = min(kc + p.flush, kb1);
           for (int kb = kc; kb < kce; ++kb, ++it) {
-            const int s = it % RAW_STAGES, l = it % LO_STAGES;
+            const int s = it % RAW_STAGES;
             mbar_wait(conv(s), (it / RAW_STAGES) & 1);
             tc_fence_after();
             const uint32_t a_hi = tmem_base + TMEM_A + s * (2 * BK), a_lo = a_hi + BK;
-            const uint32_t b_hi = sbase + s * RAW_BYTES + A_BYTES, b_lo = sbase + OFF_LO + l * B_BYTES;
+            const uint32_t b_hi = sbase + s * STAGE_BYTES + A_BYTES, b_lo = b_hi + B_BYTES;
             const uint64_t bh0 = B_MN ? umma_smem_desc(b_hi, BK * 128, 512, LAYOUT_SW128_BASE32B)
                                       : umma_smem_desc(b_hi, 16, 1024, LAYOUT_SW128);
             const uint64_t bl0 = B_MN ? umma_smem_desc(b_lo, BK * 128, 512, LAYOUT_SW128_BASE32B)
@@ -222,8 +175,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
               umma_tf32_ts(d, a_hi + j * UMMA_K, bl, idesc, 1u);
               umma_tf32_ts(d, a_hi + j * UMMA_K, bh, idesc, 1u);
             }
-            umma_commit(empty(s));    // raw stage (and its TMEM A slot) reusable once these MMAs have completed
-            umma_commit(loempty(l));  // and so is the B lo slot
+            umma_commit(empty(s));    // stage (raw tiles, B lo, TMEM A slot) reusable once these MMAs have completed
           }
           umma_commit(pfull(pb));  // partial accumulator complete
         }
@@ -238,10 +190,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       int kb0, kb1;
       krange(u % p.splits, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % RAW_STAGES, l = it % LO_STAGES;
-        const uint32_t hi = sbase + s * RAW_BYTES + A_BYTES + 16 * ct, lo = sbase + OFF_LO + l * B_BYTES + 16 * ct;
+        const int s = it % RAW_STAGES;
+        const uint32_t hi = sbase + s * STAGE_BYTES + A_BYTES + 16 * ct, lo = hi + B_BYTES;
         constexpr uint32_t CS = 16 * BCONV_THREADS;
-        mbar_wait(loempty(l), ((it / LO_STAGES) & 1) ^ 1);
+        // full(s) of this round implies the previous round's MMAs have released the stage, B lo included
         mbar_wait(full(s), (it / RAW_STAGES) & 1);
         constexpr int NB8 = B_BYTES / 16 / BCONV_THREADS / 8;
 #pragma unroll
@@ -271,7 +223,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       krange(u % p.splits, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % RAW_STAGES;
-        const uint32_t sa = sbase + s * RAW_BYTES;
+        const uint32_t sa = sbase + s * STAGE_BYTES;
         mbar_wait(full(s), (it / RAW_STAGES) & 1);
         uint32_t h[32], w[32];
         if (!A_MN) {
@@ -309,7 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
     // ------------------------------------------------------------------ accumulate + epilogue (256 threads)
     const int q = warp & 3, hc = (warp - 8) >> 2;  // TMEM lane quarter, column half
     const uint32_t st = sbase + OFF_STAGING + (warp - 8) * (32 * 33 * 4);
-    uint32_t pc = 0;
+    uint32_t pc = 0, gphase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int split = u % p.splits, tile = u / p.splits;
       const int mb = tile % p.mtiles, nb = tile / p.mtiles;
@@ -340,18 +292,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       const int ncol0 = nb * BN + hc * NC;
       if (ncol0 >= p.N) continue;
       if (p.vec) {
-        if (m_base + lane < p.M) {
-          const size_t m = (size_t)(m_base + lane);
-          const bool ab = p.bias && split == 0;
+        // TMA epilogue: this warp's 32 rows x 64 columns leave as two 32 x 32 boxes.  Box in shared memory: row = 128
+        // bytes, 16-byte chunk c of row r at chunk c ^ (r & 7) (SWIZZLE_128B: every quarter warp hits eight distinct
+        // chunks).  The gate box (activation backward) arrives the same way and is consumed before it is overwritten.
+        const uint32_t box = sbase + OFF_STAGING + (warp - 8) * 4096;
+        const uint32_t rowa = box + lane * 128;
+        const bool ab = p.bias && split == 0;
+#pragma unroll
+        for (int c = 0; c < NC / 32; ++c) {
+          const int n0 = ncol0 + c * 32;
+          if (n0 >= p.N) break;  // warp-uniform
           if (p.gate) {
-            if (p.splits > 1) epilogue_row<2, true>(p, acc, m, ncol0, ab);
-            else if (p.accumulate) epilogue_row<1, true>(p, acc, m, ncol0, ab);
-            else epilogue_row<0, true>(p, acc, m, ncol0, ab);
-          } else {
-            if (p.splits > 1) epilogue_row<2, false>(p, acc, m, ncol0, ab);
-            else if (p.accumulate) epilogue_row<1, false>(p, acc, m, ncol0, ab);
-            else epilogue_row<0, false>(p, acc, m, ncol0, ab);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(gbar(warp - 8), 4096);
+              tma_load_2d(box, &tmG, gbar(warp - 8), n0, m_base);
+            }
+            mbar_wait(gbar(warp - 8), gphase);
+            gphase ^= 1;
           }
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float x[4] = {acc[c * 32 + 4 * c4], acc[c * 32 + 4 * c4 + 1], acc[c * 32 + 4 * c4 + 2], acc[c * 32 + 4 * c4 + 3]};
+            if (ab) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) x[k] += (n0 + 4 * c4 + k < p.N) ? __ldg(p.bias + n0 + 4 * c4 + k) : 0.f;
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) x[k] = fmaxf(x[k], 0.f);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) x[k] = x[k] > 0.f ? x[k] : 0.01f * x[k];
+            }
+            const uint32_t a16 = rowa + ((c4 ^ (lane & 7)) << 4);
+            if (p.gate) {
+              const float4 g = lds128(a16);
+              x[0] *= g.x > 0.f ? 1.f : p.gslope; x[1] *= g.y > 0.f ? 1.f : p.gslope;
+              x[2] *= g.z > 0.f ? 1.f : p.gslope; x[3] *= g.w > 0.f ? 1.f : p.gslope;
+            }
+            sts128(a16, make_float4(x[0], x[1], x[2], x[3]));   // own chunk: read (gate) before write, same thread
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.splits > 1 || p.accumulate) tma_reduce_add_2d(&tmC, box, n0, m_base);
+            else tma_store_2d(&tmC, box, n0, m_base);
+            bulk_commit();
+            bulk_wait_read0();   // the box is reused by the next pass / tile
+          }
+          __syncwarp();
         }
         continue;
       }
@@ -384,6 +373,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       }
     }
   }
+  if (warp >= 8 && lane == 0) bulk_wait_all();   // this warp's TMA stores have been performed
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -445,9 +435,10 @@ int make_map(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer,
 }
 
 template <bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t s) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tg,
+           const GemmParams& p, int grid, cudaStream_t s) {
   NB_SET_SMEM_ONCE((k_gemm_tc<A_MN, B_MN>), SMEM_BYTES);
-  k_gemm_tc<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, p);
+  k_gemm_tc<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, tc, tg, p);
   NB_LAUNCH_CHECK("gemm_tc");
 }
 
@@ -479,7 +470,7 @@ int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, 
   p.splits = splits;
   // k-blocks accumulated in TMEM before the partial is folded into the fp32 registers: short reductions go in
   // one piece (the epilogue then overlaps the next tile), deep ones in chains of 4 x 12 MMAs
-  { const int kpu = cdiv(p.kblocks, splits); p.flush = kpu <= 8 ? 8 : (kpu <= 64 ? 2 : 4); }
+  { const int kpu = cdiv(p.kblocks, splits); p.flush = kpu <= 8 ? 8 : 4; }
   static const int flush_env = [] { const char* e = getenv("NEMO_B200_GEMM_FLUSH"); return e ? atoi(e) : 0; }();
   if (flush_env > 0) p.flush = flush_env;   // experiment knob: k-blocks per TMEM partial
   p.vec = (((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && (!gate || (((uintptr_t)gate & 15) == 0 && (ldg & 3) == 0))) ? 1 : 0;
@@ -492,13 +483,24 @@ int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, 
   // B: transB=1 -> stored (N,K), K-major; transB=0 -> stored (K,N), N contiguous (MN-major)
   rc = transB ? make_map(&tb, B, K, N, ldb, BN, false) : make_map(&tb, B, N, K, ldb, BK, true);
   if (rc) return rc;
+  // epilogue tensor maps: C (store / reduce-add) and the gate, 32 x 32 boxes; unused (copies of A's map) on the
+  // unaligned path
+  CUtensorMap tc = ta, tg = ta;
+  if (p.vec) {
+    rc = make_map(&tc, C, N, M, ldc, 32, false);
+    if (rc) return rc;
+    if (gate) {
+      rc = make_map(&tg, gate, N, M, ldg, 32, false);
+      if (rc) return rc;
+    }
+  }
   const int grid = min(tiles * splits, sms);
   if (transA) {
-    if (transB) return launch<true, false>(ta, tb, p, grid, s);
-    return launch<true, true>(ta, tb, p, grid, s);
+    if (transB) return launch<true, false>(ta, tb, tc, tg, p, grid, s);
+    return launch<true, true>(ta, tb, tc, tg, p, grid, s);
   }
-  if (transB) return launch<false, false>(ta, tb, p, grid, s);
-  return launch<false, true>(ta, tb, p, grid, s);
+  if (transB) return launch<false, false>(ta, tb, tc, tg, p, grid, s);
+  return launch<false, true>(ta, tb, tc, tg, p, grid, s);
 }
 
 }  // namespace nb

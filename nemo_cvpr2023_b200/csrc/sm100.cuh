@@ -84,6 +84,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// 2-D tiled store shared -> global (the box is clipped at the tensor's bounds); tracked by the issuing thread's bulk
+// async-group.  `_add`: element-wise fp32 reduction performed at the L2 (C += tile), same addressing.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // 1-D bulk async copy global -> shared (16-byte aligned addresses and size); completes `bytes` on the mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -111,6 +111,15 @@ class ParamGroup:
             self.ticket = torch.zeros(1, dtype=torch.int32, device=self.p.device)
         adam_multi(self.segments(skip_lag), self.ticket)
 
+    def fresh_alias(self):
+        """A second optimiser over the SAME parameters and gradients with its own zeroed moments and step count (the
+        reference's throw-away camera Adam, nemo/neural_motion_model.py:2869-2876)."""
+        import copy
+        a = copy.copy(self)
+        a.m, a.v, a.step_dev = torch.zeros_like(self.m), torch.zeros_like(self.v), torch.zeros_like(self.step_dev)
+        a.ticket = torch.zeros(1, dtype=torch.int32, device=self.p.device)
+        return a
+
     def reset_state(self):
         self.m.zero_(), self.v.zero_(), self.step_dev.zero_()
         if hasattr(self, 'step_lag_dev'):
@@ -244,6 +253,7 @@ class FitEngine:
         self._ws = {}
         self.training = False
         self.world, self.loss_scale, self.dp_defer = 1, 1.0, False
+        self.use_graph, self._graphs = True, {}
 
     def enable_data_parallel(self, world_size, group=None, reduce_all=False, overlap=True):
         """Shard by video instance: this rank owns its views' cameras, instance codes and
@@ -419,15 +429,17 @@ class FitEngine:
 
     # ------------------------------------------------------------------ the step
     @_on_device
-    def forward_backward(self, view_idx, frame_idx, update=True, phases=None, mode='step', detach_pose=False):
+    def forward_backward(self, view_idx, frame_idx, update=True, phases=None, mode='step', detach_pose=False,
+                         _indices_loaded=False):
         """mode: 'step' (all losses), 'warmup' (3D pose loss only), 'opt_cam' (V4: 2D + 3D, pose detached),
         'cam_fit' (MultiViewModel.opt_cam: plain-mean reprojection loss only)."""
         a, C, ro = self.args, self.C_, self.ro
         N = int(view_idx.shape[0])
         w = self.ws(N)
         Np, h = N + 1, self.h
-        w['vi'].copy_(view_idx, non_blocking=True)
-        w['fi'].copy_(frame_idx, non_blocking=True)
+        if not _indices_loaded:
+            w['vi'].copy_(view_idx, non_blocking=True)
+            w['fi'].copy_(frame_idx, non_blocking=True)
         vi, fi = w['vi'], w['fi']
         if phases is None:
             torch.index_select(self.phase_table, 0, fi, out=w['raw'])
@@ -640,6 +652,48 @@ class FitEngine:
                       w['yn'], w['dX'], self.ldx, gv['phase_rbf.log_sigmas'] if self.D > 0 else None, gg['shifts'],
                       gg['scales'], self.g_inst.gviews['learned_instance_code'] if self.g_inst else None, w['gy01'], N,
                       self.V)
+
+    @_on_device
+    def step_graph(self, view_idx, frame_idx, mode='step', detach_pose=False, which=None, skip_lag=False):
+        """forward + backward + every optimiser as ONE CUDA-graph launch: ~90 kernel launches and
+        the ATen fills / copies between them collapse into a single cudaGraphLaunch, which removes the host-side launch
+        cost that separates the end-to-end rate from the device-timed one.  The first call with a new key (batch size,
+        mode, training flag, optimiser hyper-parameters -- the learning rates are baked into the launch parameters, a
+        plateau scheduler that changes one simply causes a re-capture) runs eagerly, the second captures, later ones
+        replay.  The indices are copied into their fixed workspace slots outside the graph.  Not used under data
+        parallelism (NCCL calls stay eager) or when per-entry-point profiling is on."""
+        N = int(view_idx.shape[0])
+        w = self.ws(N)
+        w['vi'].copy_(view_idx, non_blocking=True)
+        w['fi'].copy_(frame_idx, non_blocking=True)
+        groups = which or self.groups()
+        key = (N, mode, bool(detach_pose), bool(self.training), bool(skip_lag), bool(self.compute_betas_grad),
+               tuple((id(g), g.lr, g.wd, g.betas, g.eps, g.decoupled) for g in groups))
+
+        def body():
+            out = self.forward_backward(w['vi'], w['fi'], update=True, mode=mode, detach_pose=detach_pose,
+                                        _indices_loaded=True)
+            self.optimizer_step(groups, skip_lag=skip_lag)
+            return out
+
+        if self.world > 1 or lib.profile is not None or not self.use_graph:
+            return body()
+        ent = self._graphs.get(key)
+        if ent is None:                       # first sight of this key: the eager run doubles as the warm-up
+            self._graphs[key] = 'warm'
+            return body()
+        if ent == 'warm':
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(g):
+                out = body()
+            ent = self._graphs[key] = (g, out)
+        ent[0].replay()
+        return ent[1]
+
+    def drop_graphs(self, group):
+        """forget the captured steps that reference `group`'s buffers"""
+        self._graphs = {k: v for k, v in self._graphs.items() if not any(t[0] == id(group) for t in k[-1])}
 
     @_on_device
     def optimizer_step(self, which=None, skip_lag=False):

@@ -516,9 +516,15 @@ class MultiViewModel(nn.Module):
         if not (self.args.batch_size > -1 and not full_batch):
             view_idx, frame_idx = self._full_indices()
         vi, fi = self._idx(view_idx), self._idx(frame_idx)
-        w, norm = e.forward_backward(vi, fi, update=update, mode='step')
-        if update:
-            self._step_optimizers()
+        fused = update and all(isinstance(o, FusedAdam) for o in self.optimizers)
+        if fused:      # forward + backward + Adam as one CUDA-graph launch (eager under data parallelism)
+            for o in self.optimizers:
+                o.sync_hyper()
+            w, norm = e.step_graph(vi, fi, mode='step', which=[o._g for o in self.optimizers])
+        else:
+            w, norm = e.forward_backward(vi, fi, update=update, mode='step')
+            if update:
+                self._step_optimizers()
         ld = e.loss_dict(w, norm)
         loss_dict = {k: ld[k] for k in self._LOSS_KEYS}
         if update and self.args.lr_factor < 1:
@@ -557,9 +563,10 @@ class MultiViewModel(nn.Module):
         losses = []
         for _ in range(warmup_steps):
             vi, fi = self._sample()
-            w, _ = e.forward_backward(vi, fi, update=True, mode='warmup')
             # linear_out.* get no gradient here: torch.optim.Adam skips them (no weight decay, no state, step stays 0)
-            self._step_optimizers([self.opt_motion, self.opt_phase], skip_lag=True)
+            for o in (self.opt_motion, self.opt_phase):
+                o.sync_hyper()
+            w, _ = e.step_graph(vi, fi, mode='warmup', which=[self.opt_motion._g, self.opt_phase._g], skip_lag=True)
             losses.append(w['acc'][2].clone())   # `acc` is a reused workspace slot
         return [float(x) for x in torch.stack(losses).cpu()]
 
@@ -569,19 +576,16 @@ class MultiViewModel(nn.Module):
         vi, fi = torch.arange(self.num_views), torch.zeros(self.num_views, dtype=torch.long)
         e.training = self.training
         # the reference builds a throw-away Adam here (:2873-2876): self.opt_cameras starts fresh afterwards, so the
-        # camera-fit moments live in temporary buffers and the real ones are untouched
-        g = e.g_cam
-        keep = (g.m, g.v, g.step_dev, g.lr)
-        g.m, g.v, g.step_dev = torch.zeros_like(g.m), torch.zeros_like(g.v), torch.zeros_like(g.step_dev)
-        g.lr = self.args.lr_camera
+        # camera fit runs on an alias of the camera buffers with its own moments and step count
+        tmp = e.g_cam.fresh_alias()
+        tmp.lr = self.args.lr_camera
         log = []
         try:
             for _ in range(cam_opt_steps):
-                w, _ = e.forward_backward(vi, fi, update=True, mode='cam_fit')
-                g.adam_step()
+                w, _ = e.step_graph(vi, fi, mode='cam_fit', which=[tmp])
                 log.append(w['acc'][4].clone())
         finally:
-            g.m, g.v, g.step_dev, g.lr = keep
+            e.drop_graphs(tmp)
         return [np.asarray(x) for x in torch.stack(log).cpu().numpy()] if log else []
 
 
@@ -617,8 +621,9 @@ class NemoV4(NemoV3):
         e.training = self.training
         for _ in range(cam_opt_steps):
             vi, fi = self._sample()
-            e.forward_backward(vi, fi, update=True, mode='opt_cam', detach_pose=True)
-            self._step_optimizers()
+            for o in self.optimizers:
+                o.sync_hyper()
+            e.step_graph(vi, fi, mode='opt_cam', detach_pose=True, which=[o._g for o in self.optimizers])
 
 
 class NemoV0(MultiViewModel):

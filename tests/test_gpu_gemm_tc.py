@@ -101,3 +101,49 @@ def test_gemm_dispatch_agrees_with_cuda_core_kernel(lib):
     lib.gemm(A, B, None, C1, M, N, K, K, N, N, 0, 0, 0, None, 0, 0.0, 0)
     lib.gemm_simt(A, B, None, C2, M, N, K, K, N, N, 0, 0, 0, None, 0, 0.0, 0)
     assert (C1 - C2).abs().max().item() < 4e-6 * C2.abs().max().item()
+
+
+def test_gemm_tc_tma_epilogue(lib):
+    """16-byte addressable C and gate: the tile leaves through the swizzled shared-memory box and TMA store /
+    reduce-add (ragged M and N tails are clipped by the tensor map); gate box fetched by TMA."""
+    r = np.random.RandomState(21)
+    M, N, K = 1030, 1000, 520
+    A = r.standard_normal((M, K)).astype(np.float32)
+    B = r.standard_normal((N, K)).astype(np.float32)
+    bias = r.standard_normal(N).astype(np.float32)
+    gate = r.standard_normal((M, N)).astype(np.float32)
+    C0 = r.standard_normal((M, 1004)).astype(np.float32)
+    acc = A.astype(np.float64) @ B.T.astype(np.float64)
+    Ad, Bd, Gd = G(A), G(B), G(gate)
+    scale = np.abs(acc).max()
+    # store: bias + relu
+    C = torch.full((M, N), 7.0, device=DEV)
+    lib.gemm_tc(Ad, Bd, G(bias), C, M, N, K, K, K, N, 0, 1, 1, None, 0, 0.0, 0, 1)
+    assert np.abs(npy(C) - np.maximum(acc + bias, 0)).max() / scale < 4e-6
+    # store: gate (ReLU backward, slope 0) into a strided C; the columns beyond N stay untouched
+    Cs = G(C0)
+    lib.gemm_tc(Ad, Bd, None, Cs, M, N, K, K, K, 1004, 0, 1, 0, Gd, N, 0.0, 0, 1)
+    ref = C0.astype(np.float64).copy()
+    ref[:, :N] = acc * (gate > 0)
+    assert np.abs(npy(Cs) - ref).max() / scale < 4e-6
+    # reduce-add: accumulate, leaky gate, with and without split-K
+    for splits in (1, 3):
+        Cs = G(C0)
+        lib.gemm_tc(Ad, Bd, None, Cs, M, N, K, K, K, 1004, 0, 1, 0, Gd, N, 0.01, 1, splits)
+        ref = C0.astype(np.float64).copy()
+        ref[:, :N] += acc * np.where(gate > 0, 1.0, 0.01)
+        assert np.abs(npy(Cs) - ref).max() / scale < 4e-6, 'splits=%d' % splits
+    # split-K overwrite + bias
+    Cs = G(C0)
+    lib.gemm_tc(Ad, Bd, G(bias), Cs, M, N, K, K, K, 1004, 0, 1, 0, None, 0, 0.0, 0, 4)
+    ref = C0.astype(np.float64).copy()
+    ref[:, :N] = acc + bias
+    assert np.abs(npy(Cs) - ref).max() / scale < 4e-6
+    # a persistent CTA walking many tiles (36 per SM) reuses its boxes: pose-blend shape, MN-major B
+    M2, N2, K2 = 2048, 20736, 207
+    A2 = r.standard_normal((M2, 208)).astype(np.float32)
+    B2 = (0.01 * r.standard_normal((K2, N2))).astype(np.float32)
+    C = torch.empty(M2, N2, device=DEV)
+    lib.gemm_tc(G(A2), G(B2), None, C, M2, N2, K2, 208, N2, N2, 0, 0, 0, None, 0, 0.0, 0, 0)
+    ref = A2[:, :K2].astype(np.float64) @ B2.astype(np.float64)
+    assert np.abs(npy(C) - ref).max() / np.abs(ref).max() < 4e-6
