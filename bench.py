@@ -41,6 +41,7 @@ CONFIGS = {
             what='NeMo-MoCap scale fit: 8 actions (8 parameter sets) x 8 instances x 128 frames, instances cut over the '
                  'ranks, ONE all-reduce of the 8 x 9 MB shared gradients'),
     3: dict(tag='configs[3]', version=4, actions=1, V=64, F=512, h=1024, weak=False,
+            over=dict(weight_3d_loss=1000.0),   # the reference's V3 / V4 step only runs with a 3D-loss weight (:3892)
             what='large-batch fit: 64 instances x 512 frames = 32768 samples, motion MLP width 1024, per-instance '
                  'trainable cameras (NemoV4)'),
     4: dict(tag='configs[4]', version=3, actions=1, V=16, F=256, h=1000, weak=False,
@@ -414,16 +415,14 @@ def _run_gpu(a, rank, local, world, dev):
 
     if multi:
         def dev_step():
-            multi.forward_backward([vi_d] * A, [fi_d] * A, update=True)
-            multi.optimizer_step()
+            multi.train_step([vi_d] * A, [fi_d] * A)
 
         def e2e_step():
             multi.step([vi_h] * A, [fi_h] * A)
     else:
-        def dev_step():      # inputs resident in HBM, no host read-back
+        def dev_step():      # inputs resident in HBM, no host read-back; one CUDA-graph launch on one GPU
             eng.training = train
-            eng.forward_backward(vi_d, fi_d, update=True, mode='step')
-            eng.optimizer_step()
+            eng.step_graph(vi_d, fi_d, mode='step')
 
         def e2e_step():      # the public call: pinned host indices in, loss dict out
             model.step(vi_h, fi_h)

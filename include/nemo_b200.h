@@ -90,14 +90,23 @@ int nemo_b200_rodrigues_bwd(const float* aa, int lda, const float* dR, int ldr, 
 int nemo_b200_pose_feature(const float* R, float* F, int ldf, int N, void* stream);
 
 /* ---------------------------------------------------------------- kinematic chain (K6)
- * batch_rigid_transform + transform_mat, lbs.py:337-404.  One thread per frame.
+ * batch_rigid_transform + transform_mat, lbs.py:337-404.  One warp per frame (lane = joint), the tree walked by depth;
+ * any tree (parent < 0 = root).
  * R (N,24,9); J (24,3) shared (j_stride 0) or (N,24,3) (j_stride 72); parents int32[24].
  * out: A (N,24,12) relative 3x4 transforms, JP (N,24,3) posed joints. */
 int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride, const int* parents,
                         float* A, float* JP, int N, void* stream);
+/* chain_fwd fused with what precedes it for one mesh (one launch instead of four): optionally the Rodrigues map of
+ * the 23 body joints (aa != NULL: rows of `lda` floats, 69 used; kind as in nemo_b200_rodrigues_fwd; the root rotation is
+ * copied from R0 (N,24,9), joint 0; all 24 rotations are written to R_out (N,24,9) if not NULL) -- else R (N,24,9) is
+ * the input -- and optionally the pose feature (R[1:] - I) into F[n*ldf + 0..206] (lbs.py:221-228).  Exactly one of R
+ * and aa is given.  One warp per frame, lane = joint. */
+int nemo_b200_pose_chain_fwd(const float* R, const float* aa, int lda, int kind, const float* R0,
+                             const float* J, int j_stride, const int* parents,
+                             float* R_out, float* F, int ldf, float* A, float* JP, int N, void* stream);
 /* dA (N,24,12) and dAt (N,12,24) (the same gradient transposed per frame) are summed;
  * either may be NULL.  dR (N,24,9) overwritten; dJ (N,24,3) overwritten when j_stride != 0, else (24,3)
- * ACCUMULATED with atomics (caller zeroes). */
+ * ACCUMULATED with atomics (caller zeroes); dJ may be NULL (not computed). */
 int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents,
                         const float* dA, const float* dAt, const float* dJP, float* dR, float* dJ, int N,
                         void* stream);
@@ -288,6 +297,11 @@ int nemo_b200_adam_multi(const nemo_b200_adam_seg* segs, int nseg, int* ticket, 
 int nemo_b200_act_bwd(const float* dy, const float* y, float* out, size_t n, int act, void* stream);
 int nemo_b200_scale_add(float* y, const float* x, float a, size_t n, void* stream);       /* y += a*x */
 int nemo_b200_combine_losses(const float* terms, const float* weights, int n, float* out, void* stream);
+/* Gradient rows of the (N+1, 147) MotionNet output beyond the 144 rot6d columns (the fit models subtract the phase-0
+ * translation, trans - trans_0, nemo/neural_motion_model.py:3755-3766; row N of the MLP batch is that phase-0 sample):
+ *   dY[n, 144:147] = dtrans[n],  dY[n, 147..ldy) = 0  (n < N);   dY[N, 0:144] = 0,  dY[N, 144:147] = -sum_n dtrans[n].
+ * dtrans (N,3) may be NULL (= zeros).  Columns 0..143 of rows n < N belong to nemo_b200_rot6d_bwd. */
+int nemo_b200_dy_tail(const float* dtrans, float* dY, int ldy, int N, void* stream);
 
 #ifdef __cplusplus
 }

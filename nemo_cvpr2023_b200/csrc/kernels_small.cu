@@ -151,181 +151,7 @@ extern "C" int nemo_b200_pose_feature(const float* R, float* F, int ldf, int N, 
   NB_LAUNCH_CHECK("pose_feature");
 }
 
-// =============================================================================== kinematic chain
-// The rows of the 3x4 world transforms evolve independently down the tree (G_i[r,:] = G_p[r,:] . [R_i | t_i]), so a
-// frame is handled by a group of four lanes: lane r < 3 carries row r of all 24 transforms (96 floats of local
-// memory), lane 3 idles.  4x the threads of a thread-per-frame kernel (N = 4096 is otherwise 128 warps on 148 SMs) and
-// a quarter of the serial work; the backward's sums over rows (dR_i, dt_i, dJ_i) are two butterfly shuffles.
-constexpr int CH_THREADS = 64;   // 16 frames per CTA
-constexpr int CH_FRAMES = CH_THREADS / 4;
-
-// the CTA's rotations / joints / upstream gradients are staged in shared memory with coalesced loads first: the walk
-// down the tree is a chain of dependent accesses, and from global memory each of its 24 steps would pay a DRAM / L2
-// latency
-__device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int count) {
-  for (int i = threadIdx.x; i < count; i += CH_THREADS) dst[i] = __ldg(src + i);
-}
-
-__device__ __forceinline__ float quad_sum(float v) {  // sum over the four lanes of a frame group
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v;
-}
-
-// row r of the world transforms of one frame: Grow[i][0..3]
-__device__ __forceinline__ void chain_rows(const float* __restrict__ R, const float* __restrict__ J, const int* sp, int r,
-                                           float (&Grow)[NJ][4]) {
-#pragma unroll 1
-  for (int i = 0; i < NJ; ++i) {
-    const float* Ri = R + 9 * i;
-    const int p = sp[i];
-    if (i == 0 || p < 0) {
-      Grow[i][0] = Ri[3 * r]; Grow[i][1] = Ri[3 * r + 1]; Grow[i][2] = Ri[3 * r + 2];
-      Grow[i][3] = J[3 * i + r];
-    } else {
-      const float g0 = Grow[p][0], g1 = Grow[p][1], g2 = Grow[p][2];
-      const float t0 = J[3 * i] - J[3 * p], t1 = J[3 * i + 1] - J[3 * p + 1], t2 = J[3 * i + 2] - J[3 * p + 2];
-      Grow[i][0] = g0 * Ri[0] + g1 * Ri[3] + g2 * Ri[6];
-      Grow[i][1] = g0 * Ri[1] + g1 * Ri[4] + g2 * Ri[7];
-      Grow[i][2] = g0 * Ri[2] + g1 * Ri[5] + g2 * Ri[8];
-      Grow[i][3] = g0 * t0 + g1 * t1 + g2 * t2 + Grow[p][3];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(CH_THREADS) k_chain_fwd(const float* __restrict__ R, const float* __restrict__ J, int js,
-                                                          const int* __restrict__ parents, float* __restrict__ A,
-                                                          float* __restrict__ JP, int N) {
-  __shared__ int sp[NJ];
-  __shared__ float sR[CH_FRAMES * 216], sJ[CH_FRAMES * 72];
-  if (threadIdx.x < NJ) sp[threadIdx.x] = parents[threadIdx.x];
-  const int n0 = blockIdx.x * CH_FRAMES, nf = min(CH_FRAMES, N - n0);
-  stage(sR, R + (size_t)n0 * 216, nf * 216);
-  stage(sJ, J + (size_t)n0 * js, js ? nf * 72 : 72);
-  __syncthreads();
-  const int f = threadIdx.x >> 2, n = n0 + f, r = threadIdx.x & 3;
-  if (n >= N || r == 3) return;
-  const float* Rn = sR + f * 216;
-  const float* Jn = sJ + f * js;
-  float G[NJ][4];
-  chain_rows(Rn, Jn, sp, r, G);
-  float* An = A + (size_t)n * 288 + 4 * r;
-  float* JPn = JP + (size_t)n * 72 + r;
-#pragma unroll 1
-  for (int i = 0; i < NJ; ++i) {
-    const float a3 = G[i][3] - (G[i][0] * Jn[3 * i] + G[i][1] * Jn[3 * i + 1] + G[i][2] * Jn[3 * i + 2]);
-    *reinterpret_cast<float4*>(An + 12 * i) = make_float4(G[i][0], G[i][1], G[i][2], a3);
-    JPn[3 * i] = G[i][3];
-  }
-}
-
-__global__ void __launch_bounds__(CH_THREADS) k_chain_bwd(const float* __restrict__ R, const float* __restrict__ J, int js,
-                                                          const int* __restrict__ parents, const float* __restrict__ dA,
-                                                          const float* __restrict__ dAt, const float* __restrict__ dJP,
-                                                          float* __restrict__ dR, float* __restrict__ dJ, int N) {
-  __shared__ int sp[NJ];
-  __shared__ float sdj[CH_THREADS / 32][NJ * 3];
-  __shared__ float sR[CH_FRAMES * 216], sJ[CH_FRAMES * 72], sdA[CH_FRAMES * 288];
-  if (threadIdx.x < NJ) sp[threadIdx.x] = parents[threadIdx.x];
-  const int n0 = blockIdx.x * CH_FRAMES, nf = min(CH_FRAMES, N - n0);
-  stage(sR, R + (size_t)n0 * 216, nf * 216);
-  stage(sJ, J + (size_t)n0 * js, js ? nf * 72 : 72);
-  if (dA) stage(sdA, dA + (size_t)n0 * 288, nf * 288);
-  __syncthreads();
-  const int f = threadIdx.x >> 2, n = n0 + f, r = threadIdx.x & 3;
-  const bool live = n < N, row = live && r < 3;   // lane 3 and frames past the end contribute zeros to every sum
-  const int nn = live ? n : N - 1, ff = live ? f : nf - 1, rr = r < 3 ? r : 0;
-  const float* Rn = sR + ff * 216;
-  const float* Jn = sJ + ff * js;
-  float G[NJ][4], dG[NJ][4];
-  float dJl[NJ];  // lane a < 3 accumulates component a of dJ
-  chain_rows(Rn, Jn, sp, rr, G);
-  const float* dAn = dA ? sdA + ff * 288 : nullptr;
-  const float* dAtn = dAt ? dAt + (size_t)nn * 288 : nullptr;
-  const float* dJPn = dJP ? dJP + (size_t)nn * 72 : nullptr;
-#pragma unroll 1
-  for (int i = 0; i < NJ; ++i) {
-    float a[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      a[c] = row ? (dAn ? dAn[12 * i + 4 * rr + c] : 0.f) + (dAtn ? dAtn[(4 * rr + c) * NJ + i] : 0.f) : 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) dG[i][c] = a[c] - a[3] * Jn[3 * i + c];
-    dG[i][3] = a[3] + ((row && dJPn) ? dJPn[3 * i + rr] : 0.f);
-    // dJ_i[c] = - sum_r G_i[r][c] a3_r
-    const float s0 = quad_sum(G[i][0] * a[3]), s1 = quad_sum(G[i][1] * a[3]), s2 = quad_sum(G[i][2] * a[3]);
-    dJl[i] = -(r == 0 ? s0 : (r == 1 ? s1 : s2));
-  }
-  float* dRn = dR + (size_t)nn * 216;
-#pragma unroll 1
-  for (int i = NJ - 1; i >= 1; --i) {
-    const int p = sp[i];
-    const float* Ri = Rn + 9 * i;
-    const float t0 = Jn[3 * i] - Jn[3 * p], t1 = Jn[3 * i + 1] - Jn[3 * p + 1], t2 = Jn[3 * i + 2] - Jn[3 * p + 2];
-    const float d0 = dG[i][0], d1 = dG[i][1], d2 = dG[i][2], d3 = dG[i][3];
-    // dR_i[a][b] = sum_r Gp[r][a] dG_i[r][b] ; dt[a] = sum_r Gp[r][a] dG_i[r][3]   (sums over the row lanes)
-    float m[3][4];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float g = G[p][a];
-      m[a][0] = quad_sum(g * d0); m[a][1] = quad_sum(g * d1); m[a][2] = quad_sum(g * d2); m[a][3] = quad_sum(g * d3);
-    }
-    const float* mr = r == 0 ? m[0] : (r == 1 ? m[1] : m[2]);
-    if (row) {
-      dRn[9 * i + 3 * r] = mr[0]; dRn[9 * i + 3 * r + 1] = mr[1]; dRn[9 * i + 3 * r + 2] = mr[2];
-    }
-    dJl[i] += mr[3];
-    dJl[p] -= mr[3];
-    // dGp[r][c] += dG_i[r][0..2] . R_i[c][0..2] + dG_i[r][3] t[c] ; dGp[r][3] += dG_i[r][3]
-    dG[p][0] += d0 * Ri[0] + d1 * Ri[1] + d2 * Ri[2] + d3 * t0;
-    dG[p][1] += d0 * Ri[3] + d1 * Ri[4] + d2 * Ri[5] + d3 * t1;
-    dG[p][2] += d0 * Ri[6] + d1 * Ri[7] + d2 * Ri[8] + d3 * t2;
-    dG[p][3] += d3;
-  }
-  if (row) {
-    dRn[3 * r] = dG[0][0]; dRn[3 * r + 1] = dG[0][1]; dRn[3 * r + 2] = dG[0][2];
-  }
-  dJl[0] += dG[0][3];
-  if (!dJ) return;
-  if (js != 0) {
-    if (row)
-#pragma unroll 1
-      for (int i = 0; i < NJ; ++i) dJ[(size_t)n * 72 + 3 * i + r] = dJl[i];
-  } else {
-    // shared joints: sum over the frames of the CTA (lanes with equal r, then the four warps), one atomic per value
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (int i = 0; i < NJ; ++i) {
-      float v = row ? dJl[i] : 0.f;
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < 3) sdj[warp][3 * i + lane] = v;
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < NJ * 3; k += CH_THREADS) {
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < CH_THREADS / 32; ++w) v += sdj[w][k];
-      atomicAdd(dJ + k, v);
-    }
-  }
-}
-extern "C" int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride, const int* parents, float* A,
-                                   float* JP, int N, void* stream) {
-  if (N == 0) return 0;
-  NB_REQUIRE(R && J && parents && A && JP && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_fwd: bad args");
-  k_chain_fwd<<<cdiv(N, CH_THREADS / 4), CH_THREADS, 0, S(stream)>>>(R, J, j_stride, parents, A, JP, N);
-  NB_LAUNCH_CHECK("chain_fwd");
-}
-extern "C" int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents, const float* dA,
-                                   const float* dAt,
-                                   const float* dJP, float* dR, float* dJ, int N, void* stream) {
-  if (N == 0) return 0;
-  NB_REQUIRE(R && J && parents && dR && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_bwd: bad args");
-  k_chain_bwd<<<cdiv(N, CH_THREADS / 4), CH_THREADS, 0, S(stream)>>>(R, J, j_stride, parents, dA, dAt, dJP, dR, dJ, N);
-  NB_LAUNCH_CHECK("chain_bwd");
-}
+// (the kinematic chain lives in chain.cu)
 
 // =============================================================================== joint gather
 __global__ void k_jgather_fwd(const float* __restrict__ JP, const float* __restrict__ JX, int nx_raw, int np,
@@ -1106,6 +932,38 @@ extern "C" int nemo_b200_act_bwd(const float* dy, const float* y, float* out, si
   NB_REQUIRE(dy && y && out && (act == 1 || act == 2), "act_bwd: bad args");
   k_act_bwd<<<cdiv((long long)n, 256), 256, 0, S(stream)>>>(dy, y, out, n, act == 1 ? 0.f : 0.01f);
   NB_LAUNCH_CHECK("act_bwd");
+}
+// see nemo_b200_dy_tail in the header; one CTA: column sums of dtrans over the N rows by block reduction
+__global__ void __launch_bounds__(256) k_dy_tail(const float* __restrict__ dtr, float* __restrict__ dY, int ldy, int N) {
+  __shared__ float red[3][256];
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float* row = dY + (size_t)n * ldy;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = dtr ? dtr[(size_t)n * 3 + c] : 0.f;
+      row[144 + c] = v;
+      s[c] += v;
+    }
+    for (int c = 147; c < ldy; ++c) row[c] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) red[c][threadIdx.x] = s[c];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) red[c][threadIdx.x] += red[c][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  float* last = dY + (size_t)N * ldy;
+  for (int c = threadIdx.x; c < ldy; c += 256) last[c] = (c >= 144 && c < 147) ? -red[c - 144][0] : 0.f;
+}
+extern "C" int nemo_b200_dy_tail(const float* dtrans, float* dY, int ldy, int N, void* stream) {
+  NB_REQUIRE(dY && ldy >= 147 && N >= 0, "dy_tail: bad args");
+  k_dy_tail<<<1, 256, 0, S(stream)>>>(dtrans, dY, ldy, N);
+  NB_LAUNCH_CHECK("dy_tail");
 }
 __global__ void k_combine(const float* __restrict__ t, const float* __restrict__ w, int n, float* __restrict__ out) {
   float s = 0.f;

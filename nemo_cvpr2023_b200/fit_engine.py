@@ -31,21 +31,35 @@ L_VP = 32      # VPoser latent size
 class ParamGroup:
     """One optimiser of the reference = one flat fp32 buffer (+ grad, Adam moments, device step count)."""
 
-    def __init__(self, specs, device, lr, weight_decay=0.0, decoupled=False):
+    @staticmethod
+    def _norm(specs):
+        return [(sp[0], tuple(sp[1]), (sp[2] if len(sp) > 2 else (sp[1][-1] if len(sp[1]) else 1))) for sp in specs]
+
+    @staticmethod
+    def _sizes(specs):
+        sizes = []
+        for _, shape, ld in ParamGroup._norm(specs):
+            k = int(np.prod(shape[:-1])) * ld if len(shape) >= 2 else int(np.prod(shape))
+            sizes.append((k + 3) // 4 * 4)
+        return sizes
+
+    @staticmethod
+    def flat_size(specs):
+        return sum(ParamGroup._sizes(specs))
+
+    def __init__(self, specs, device, lr, weight_decay=0.0, decoupled=False, storage=None):
         """specs: [(name, shape)] or [(name, shape, ld)].  Every tensor starts on a 16-byte boundary and a matrix may
         be stored with a padded row stride ld >= shape[1] (zero padding that Adam leaves at zero: zero gradient,
         zero weight), which is what the TMA-fed GEMM needs; `views` are the logical (unpadded) tensors, `padded` /
-        `gpadded` the storage handed to the kernels."""
-        self.specs = [(sp[0], tuple(sp[1]), (sp[2] if len(sp) > 2 else (sp[1][-1] if len(sp[1]) else 1))) for sp in specs]
-        sizes = []
-        for _, shape, ld in self.specs:
-            k = int(np.prod(shape[:-1])) * ld if len(shape) >= 2 else int(np.prod(shape))
-            sizes.append((k + 3) // 4 * 4)
+        `gpadded` the storage handed to the kernels.  storage = (p, g, m, v): zeroed flat slices of a buffer shared with
+        the other groups of an engine (one allocation, one gradient fill per step)."""
+        self.specs = self._norm(specs)
+        sizes = self._sizes(specs)
         n = sum(sizes)
-        self.p = torch.zeros(n, device=device)
-        self.g = torch.zeros(n, device=device)
-        self.m = torch.zeros(n, device=device)
-        self.v = torch.zeros(n, device=device)
+        if storage is None:
+            storage = tuple(torch.zeros(n, device=device) for _ in range(4))
+        self.p, self.g, self.m, self.v = storage
+        assert all(t.numel() == n for t in storage)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self.lr, self.wd, self.decoupled = float(lr), float(weight_decay), bool(decoupled)
         self.betas, self.eps = (0.9, 0.999), 1e-8
@@ -203,12 +217,28 @@ class FitEngine:
         self.IMG_D0, self.IMG_D1 = int(data['IMG_D0']), int(data['IMG_D1'])
         h, V, K = self.h, self.V, self.K
         # ---- parameters, grouped as the reference groups its optimisers
-        self.g_cam = ParamGroup([('learned_cameras', (V, 9))], self.dev, a.lr_camera)
+        # One allocation holds the parameters / gradients / moments of all optimisers, laid out
+        # [cameras | motion MLP ... RBF log_sigmas | phase networks | instance codes].  Most gradients are OVERWRITTEN by
+        # their producers every step (wgrad GEMM epilogues, column sums, cam_finish); only log_sigmas, the phase networks
+        # and the instance codes are accumulated with atomics (embed_bwd) -- they sit at the end of the motion range and
+        # right after it, so the per-step gradient fill is ONE small memset (`g_zero`) instead of one 9 MB fill per group.
+        cam_specs = [('learned_cameras', (V, 9))]
         motion = motion_specs(h, self.in_dim, self.ldx, self.D)
-        self.g_motion = ParamGroup(motion, self.dev, a.lr_human, a.wd_human, decoupled=(a.opt_human == 'adamw'))
+        phase_specs = [('shifts', (V, K)), ('scales', (V, K))]
+        inst_specs = [('learned_instance_code', (V, self.Cc))] if self.Cc else None
+        sizes = [ParamGroup.flat_size(sp) if sp else 0 for sp in (cam_specs, motion, phase_specs, inst_specs)]
+        flat = [torch.zeros(sum(sizes), device=self.dev) for _ in range(4)]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        sto = lambda i: tuple(t[offs[i]:offs[i + 1]] for t in flat)
+        self.g_cam = ParamGroup(cam_specs, self.dev, a.lr_camera, storage=sto(0))
+        self.g_motion = ParamGroup(motion, self.dev, a.lr_human, a.wd_human, decoupled=(a.opt_human == 'adamw'),
+                                   storage=sto(1))
         self.g_motion.set_lagging(LAGGING)
-        self.g_phase = ParamGroup([('shifts', (V, K)), ('scales', (V, K))], self.dev, a.lr_phase)
-        self.g_inst = ParamGroup([('learned_instance_code', (V, self.Cc))], self.dev, a.lr_instance) if self.Cc else None
+        self.g_phase = ParamGroup(phase_specs, self.dev, a.lr_phase, storage=sto(2))
+        self.g_inst = ParamGroup(inst_specs, self.dev, a.lr_instance, storage=sto(3)) if self.Cc else None
+        z0 = int(offs[1]) + (self.g_motion.offsets['phase_rbf.log_sigmas'][0] if self.D > 0 else sizes[1])
+        self.g_zero = flat[1][z0:]              # gradients accumulated with atomics
+        self.g_all = flat[1]
         self.betas = torch.zeros(1, 10, device=self.dev)
         self.betas_grad = torch.zeros(1, 10, device=self.dev)
         self.compute_betas_grad = False
@@ -362,16 +392,20 @@ class FitEngine:
             PO_m=z(N, 3 * VP), PO_o=z(N, 3 * VP), PO_r=z(N, 3 * VP), dPO=z(N, 3 * VP),
             A_m=z(N, 288), A_o=z(N, 288), A_r=z(N, 288), JP=z(N, 72), JPs=z(N, 72),
             R_o=z(N, 24, 9), R_r=z(N, 24, 9),
-            JX=z(N, max(nxr, 1), 3), Z=z(N, ldz), dZ=z(N, ldz), zb=z(ldz), dzb=z(ldz), j25=z(N, 25, 3), p2d=z(N, 25, 2), loss_all=z(N, 25, 2), view_acc=z(self.V, 2),
+            JX=z(N, max(nxr, 1), 3), Z=z(N, ldz), dZ=z(N, ldz), zb=z(ldz), dzb=z(ldz), j25=z(N, 25, 3), p2d=z(N, 25, 2), loss_all=z(N, 25, 2),
             E1=z(N, H_VP), head=z(N, 2 * L_VP), dhead=z(N, 2 * L_VP), D1=z(N, H_VP), D2=z(N, H_VP), D3=z(N, 126),
             Rdec=z(N * 21, 9), recon=z(N, 69), signs=torch.zeros(N, 3, 2, VP // 32, dtype=torch.int32, device=d),
-            ll=z(N), acc=z(8), terms=z(8), wts=z(8), total=z(1),
+            ll=z(N), terms=z(8), wts=z(8), total=z(1),
             d_aa=z(N, 72), dR=z(N, 24, 9), dR_o=z(N, 24, 9), dA=z(N, 288), dAs=z(N, 288), dJP=z(N, 72), dJX=z(N, max(nxr, 1), 3),
             dj25=z(N, 25, 3), dtr=z(N, 3), dY=z(Np, LDY), dHa=z(Np, h), dHb=z(Np, h), dX=z(Np, self.ldx),
-            dE1=z(N, H_VP), dcam=z(self.V, 12), gy01=z(self.V, 2), dJ=z(72), dJ_m=z(72), dbase=z(3 * VP),
+            dE1=z(N, H_VP), gy01=z(self.V, 2), dJ=z(72), dJ_m=z(72), dbase=z(3 * VP),
             base=z(3, VP), J=z(72), vi=torch.zeros(N, dtype=torch.long, device=d),
             fi=torch.zeros(N, dtype=torch.long, device=d), noise=z(N, max(self.Cc, 1)),
         )
+        # per-step accumulators (loss terms, per-view sums, camera gradient sums): one buffer, one fill per step
+        V = self.V
+        w['zbuf'] = z(8 + 14 * V)
+        w['acc'], w['view_acc'], w['dcam'] = w['zbuf'][:8], w['zbuf'][8:8 + 2 * V].view(V, 2), w['zbuf'][8 + 2 * V:].view(V, 12)
         self._ws[N] = w
         return w
 
@@ -408,12 +442,16 @@ class FitEngine:
         # trans - trans_0 (:3755-3766): row N of Y is the phase-0 / zero-code sample
         torch.sub(w['Y'][:N, 144:147], w['Y'][N:Np, 144:147], out=w['trans'])
 
-    def _lbs_forward(self, w, N, R, PO, A, JP):
-        """pose feature -> pose blend shapes (planar, lbs.py:221-235) and the kinematic chain (lbs.py:337-404)"""
+    def _lbs_forward(self, w, N, R, PO, A, JP, aa=None, lda=0):
+        """(Rodrigues ->) pose feature + kinematic chain in one launch (lbs.py:221-235, :337-404), then the pose blend
+        shapes (planar).  aa: the body pose as axis-angle rows; R then RECEIVES the rotations (root copied from the
+        main mesh's), as the two extra SMPL calls of vposer_loss build them (:2787-2793)."""
         C = self.C_
-        lib.pose_feature(R, w['F'], LDF, N)
+        if aa is None:
+            lib.pose_chain_fwd(R, None, 0, 0, None, w['J'], 0, C.parents, None, w['F'], LDF, A, JP, N)
+        else:
+            lib.pose_chain_fwd(None, aa, lda, 0, w['R'], w['J'], 0, C.parents, R, w['F'], LDF, A, JP, N)
         gemm(w['F'], C.PD, PO, N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
-        lib.chain_fwd(R, w['J'], 0, C.parents, A, JP, N)
 
     def _joints_forward(self, w, N):
         """The main mesh of a step is consumed only through 25 joints: kinematic joints come
@@ -421,8 +459,8 @@ class FitEngine:
         which contract the pose feature with pre-reduced blend shapes -- identical arithmetic up to fp32 summation
         order, without the 6890-vertex mesh, its 20736-wide pose-blend GEMM or the skinning kernel."""
         C, ro = self.C_, self.ro
-        lib.pose_feature(w['R'], w['F_m'], LDF, N)   # own buffer: the prior branch rewrites w['F'] concurrently
-        lib.chain_fwd(w['R'], w['J'], 0, C.parents, w['A_m'], w['JP'], N)
+        # own feature buffer: the prior branch rewrites w['F'] concurrently
+        lib.pose_chain_fwd(w['R'], None, 0, 0, None, w['J'], 0, C.parents, None, w['F_m'], LDF, w['A_m'], w['JP'], N)
         if ro['np'] + ro['nx']:
             gemm(w['F_m'], ro['MZ'], w['Z'], N, ro['ldz'], 207, LDF, ro['ldz'], ro['ldz'], bias=w['zb'])
             lib.readout_fwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['JX'], N)
@@ -445,8 +483,7 @@ class FitEngine:
             torch.index_select(self.phase_table, 0, fi, out=w['raw'])
         else:
             w['raw'].copy_(phases)
-        w['acc'].zero_()
-        w['view_acc'].zero_()
+        w['zbuf'].zero_()
         use_noise = self.version >= 3 and self.training and a.code_noise > 0 and self.Cc > 0
         self._motion_forward(w, N, vi, w['raw'], use_noise)
         self._shape(w)
@@ -468,7 +505,7 @@ class FitEngine:
 
         def branch_2d_backward():
             lib.kp_loss_bwd(w['j25'], vi, fi, self.g_cam.views['learned_cameras'], self.gt2d, self.bbox,
-                            self.focal, cx, cy, 100.0, mode_id, red, w['view_acc'], ls, w['dj25'], w['dcam'].zero_(),
+                            self.focal, cx, cy, 100.0, mode_id, red, w['view_acc'], ls, w['dj25'], w['dcam'],
                             acc[4:5], N, 25, self.V, self.F)
             lib.cam_finish(self.g_cam.views['learned_cameras'], w['dcam'], self.g_cam.gviews['learned_cameras'],
                            0, self.V)
@@ -479,7 +516,7 @@ class FitEngine:
                 lib.readout_bwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['dJX'],
                                 w['dA'], 0, w['dZ'], N)
             lib.chain_bwd(w['R'], w['J'], 0, C.parents, w['dA'] if nq else None, None, w['dJP'], dR,
-                          w['dJ_m'].zero_(), N)
+                          w['dJ_m'].zero_() if self.compute_betas_grad else None, N)
             if detach_pose:
                 # V4 opt_cam (:4060-4149): body rotmats detached, gradient reaches the MLP through the global
                 # orientation and the translation only
@@ -495,8 +532,7 @@ class FitEngine:
         overlap = (self.overlap_2d and need_2d and mode == 'step' and update and not self.compute_betas_grad
                    and lib.profile is None)
         if update:
-            for g in self.groups():
-                g.g.zero_()
+            self.g_zero.zero_()
         if overlap:
             if self._side is None:
                 self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Event(), torch.cuda.Event())
@@ -532,12 +568,8 @@ class FitEngine:
             lib.rotmat2aa_fwd(w['Rdec'], 189, w['recon'], 69, 21, N * 21, 0)
             w['recon'][:, 63:].copy_(w['aa'][:, 66:72])
             # the two extra SMPL forwards of vposer_loss (:2787-2793): quaternion Rodrigues, shared global orient
-            for key_R, src, ld in (('R_o', w['aa'].view(-1)[3:], 72), ('R_r', w['recon'], 69)):
-                Rb = w[key_R]
-                Rb[:, 0].copy_(w['R'][:, 0])
-                lib.rodrigues_fwd(src, ld, Rb.view(-1)[9:], 216, 23, N * 23, 0)
-            self._lbs_forward(w, N, w['R_o'], w['PO_o'], w['A_o'], w['JPs'])
-            self._lbs_forward(w, N, w['R_r'], w['PO_r'], w['A_r'], w['JPs'])
+            self._lbs_forward(w, N, w['R_o'], w['PO_o'], w['A_o'], w['JPs'], aa=w['aa'].view(-1)[3:], lda=72)
+            self._lbs_forward(w, N, w['R_r'], w['PO_r'], w['A_r'], w['JPs'], aa=w['recon'], lda=69)
             lib.skin_l1_fwd(w['A_o'], w['PO_o'], w['A_r'], w['PO_r'], w['base'], C.Wt, w['signs'], acc[0:1], N)
             # GMM prior (:2758-2773): value and (scaled) gradient in one pass
             lib.gmm_prior(w['aa'].view(-1)[3:], 72, self.gmm_means, self.gmm_prec, self.gmm_w, self.gmm_means.shape[0],
@@ -566,7 +598,8 @@ class FitEngine:
             if full and w_vp:
                 lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, None, w['signs'], ls * w_vp / (N * NV * 3.0),
                              w['dPO'], w['dAs'], N)
-                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, w['dAs'], None, None, w['dR_o'], w['dJ'].zero_(), N)
+                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, w['dAs'], None, None, w['dR_o'],
+                              w['dJ'].zero_() if self.compute_betas_grad else None, N)
                 gemm(w['dPO'], C.PD, w['dR_o'].view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
                      accumulate=True)
                 if self.compute_betas_grad:
@@ -580,11 +613,9 @@ class FitEngine:
                 torch.cuda.current_stream().wait_event(ev_join)
             # axis-angle outputs of the pose head -> rotation matrices -> 6D -> MLP output
             lib.rotmat2aa_bwd(w['R'], 9, w['d_aa'], 3, dR, 9, 1, 1, N * 24, 1)
-            w['dY'].zero_()
             lib.rot6d_bwd(w['Y'], LDY, dR, 216, w['dY'], LDY, 24, 0, N * 24)
-            if need_2d:
-                w['dY'][:N, 144:147].copy_(w['dtr'])
-                w['dY'][N, 144:147].copy_(w['dtr'].sum(0).neg_())
+            # translation columns, pad column and the phase-0 row of dY (trans - trans_0, :3755-3766) in one launch
+            lib.dy_tail(w['dtr'] if need_2d else None, w['dY'], LDY, N)
             self._motion_backward(w, N, vi)
             if w_inst:
                 self.g_inst.gviews['learned_instance_code'].add_(
@@ -625,11 +656,10 @@ class FitEngine:
         gb = lambda i: gv['learned_motion.net.net.%d.bias' % i]
         dY = w['dY']
         gemm(dY, w['H3'], self.gWhead, 147, h, Np, LDY, h, h, transA=True)
-        lib.colsum(dY, self.gbhead, Np, 147, LDY, 0)
-        # d/d linear_out.bias of (trans - trans_0) cancels exactly (row N of dY is minus the column sum of the
-        # rows above it); keep it an exact 0 like the reference instead of summation-order noise that Adam
-        # would amplify into lr-sized steps
-        self.gbhead[144:147].zero_()
+        # d/d linear_out.bias of (trans - trans_0) cancels exactly (row N of dY is minus the column sum of the rows above
+        # it): only the 144 rot_out columns are summed, the three linear_out.bias entries are never written and stay an
+        # exact 0 like the reference's -- not summation-order noise that Adam would amplify into lr-sized steps
+        lib.colsum(dY, self.gbhead, Np, 144, LDY, 0)
         self._dp_bucket('head')
         gemm(dY, self.Whead, w['dHa'], Np, h, 147, LDY, h, h, gate=w['H3'], ldg=h)
         gemm(w['dHa'], w['H2'], gW(4), h, h, Np, h, h, h, transA=True)

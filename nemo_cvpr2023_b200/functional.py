@@ -405,10 +405,9 @@ class _LBS(torch.autograd.Function):
             if nq:
                 zb = _new((ro['ldz'],), rot)
                 gemm(betas, ro['MZ'][207:], zb, 1, ro['ldz'], nb, nb, ro['ldz'], ro['ldz'], bias=ro['Z0'])
-        lib.pose_feature(rot, F, ldf, N)
         A = _new((N, 24, 12), rot)
         JP = _new((N, 24, 3), rot)
-        lib.chain_fwd(rot, J, js, C.parents, A, JP, N)
+        lib.pose_chain_fwd(rot, None, 0, 0, None, J, js, C.parents, None, F, ldf, A, JP, N)   # pose feature + chain
         PO = None
         V = torch.empty(0, device=dev)
         if want_vertices:

@@ -70,16 +70,41 @@ class MultiActionFit:
             self._allreduce_all()
         return outs
 
+    def train_step(self, view_idx, frame_idx):
+        """forward + backward + Adam of every action; one CUDA-graph launch per action on its own stream when the fit
+        runs on one GPU (the all-reduce of a data-parallel fit sits between backward and Adam, so that path is eager).
+        Returns the engines' (workspace, norm) pairs."""
+        if self.world > 1:
+            outs = self.forward_backward(view_idx, frame_idx, update=True)
+            self.optimizer_step()
+            return outs
+        cur = torch.cuda.current_stream(self.dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs = []
+        for m, st, vi, fi in zip(self.models, self.streams, view_idx, frame_idx):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                e = m.engine
+                e.training = m.training or m.VERSION >= 3
+                for o in m.optimizers:
+                    o.sync_hyper()
+                outs.append(e.step_graph(vi, fi, mode='step', which=[o._g for o in m.optimizers]))
+                e.training = False
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+        return outs
+
     def optimizer_step(self):
         for m in self.models:
             m._step_optimizers()
 
     def step(self, view_idx, frame_idx, update=True):
         """One iteration of every action model -> list of (loss_dict, info_dict), like `NemoV*.step`."""
-        outs = self.forward_backward([m._idx(v) for m, v in zip(self.models, view_idx)],
-                                     [m._idx(f) for m, f in zip(self.models, frame_idx)], update=update)
-        if update:
-            self.optimizer_step()
+        vi = [m._idx(v) for m, v in zip(self.models, view_idx)]
+        fi = [m._idx(f) for m, f in zip(self.models, frame_idx)]
+        outs = self.train_step(vi, fi) if update else self.forward_backward(vi, fi, update=False)
         host = self.losses_packed(outs)          # ONE device->host copy for all actions
         res = []
         for m, (w, norm), row in zip(self.models, outs, host):

@@ -142,8 +142,9 @@ class FusedAdam(torch.optim.Optimizer):
         off = (p.data_ptr() - g.p.data_ptr()) // 4
         if not (0 <= off < g.p.numel()):
             raise RuntimeError('optimizer parameter is not a view of the engine buffer')
-        m = torch.as_strided(g.m, p.shape, p.stride(), off)
-        v = torch.as_strided(g.v, p.shape, p.stride(), off)
+        # as_strided takes an offset into the underlying STORAGE; the group's buffers are slices of the engine's
+        m = torch.as_strided(g.m, p.shape, p.stride(), g.m.storage_offset() + off)
+        v = torch.as_strided(g.v, p.shape, p.stride(), g.v.storage_offset() + off)
         lag = any(lo <= off < lo + k for lo, k, lagging in g.ranges() if lagging)
         return m, v, (g.step_lag_dev if lag else g.step_dev)
 

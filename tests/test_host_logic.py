@@ -13,9 +13,14 @@ from tests.util import GOLD
 
 
 def _motion_group(h, in_dim, D):
+    """the motion optimiser's group as the engine builds it: a slice (offset != 0) of storage shared with other groups"""
     ldx = (in_dim + 3) // 4 * 4
-    g = fe.ParamGroup(fe.motion_specs(h, in_dim, ldx, D), 'cpu', 1e-3, 1e-3)
+    specs = fe.motion_specs(h, in_dim, ldx, D)
+    n = fe.ParamGroup.flat_size(specs)
+    flat = [torch.zeros(72 + n + 40) for _ in range(4)]
+    g = fe.ParamGroup(specs, 'cpu', 1e-3, 1e-3, storage=tuple(t[72:72 + n] for t in flat))
     g.set_lagging(fe.LAGGING)
+    g._flat = flat
     return g
 
 
@@ -54,6 +59,8 @@ def test_reference_optimizer_state_lands_in_the_flat_buffers():
             assert torch.equal(g.m[o:o + k], ref_m.reshape(-1)) and torch.equal(g.v[o:o + k], ref_v.reshape(-1)), n
             used[o:o + k] = True
     assert float(g.m[~used].abs().sum()) == 0.0 and float(g.v[~used].abs().sum()) == 0.0
+    for t in g._flat[2:]:   # nothing spilled into the neighbouring groups' slices
+        assert float(t[:72].abs().sum()) == 0.0 and float(t[72 + g.m.numel():].abs().sum()) == 0.0
     back = opt.state_dict()
     assert sorted(back['state']) == sorted(sd['state'])
     for i in sd['state']:
