@@ -64,6 +64,7 @@ struct GemmParams {
   const float* bias;
   const float* gate;
   float* C;
+  unsigned long long* dbg;   // NEMO_B200_GEMM_TIMING: clock stamps of CTA 0 (see gemm_timing_report)
 };
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -86,6 +87,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   auto gbar = [&](int w) { return bars + 8u * (3 * RAW_STAGES + 8 + w); };   // gate box of epilogue warp w landed (tx)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto stamp = [&](int i) {
+    if (p.dbg && blockIdx.x == 0) p.dbg[i] = (unsigned long long)clock64();
+  };
+  if (threadIdx.x == 0) stamp(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -106,6 +111,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32u(tmem_slot);
+  if (threadIdx.x == 0) stamp(1);
 
   const int units = p.mtiles * p.ntiles * p.splits;
   constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, B_MN ? 1 : 0);  // A is K-major in TMEM whatever its source
@@ -126,6 +132,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % RAW_STAGES;
           mbar_wait(empty(s), ((it / RAW_STAGES) & 1) ^ 1);
+          if (it == 0) stamp(2);
           mbar_arrive_expect_tx(full(s), RAW_BYTES);
           const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
           if (!A_MN) {
@@ -160,6 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
           for (int kb = kc; kb < kce; ++kb, ++it) {
             const int s = it % RAW_STAGES;
             mbar_wait(conv(s), (it / RAW_STAGES) & 1);
+            if (it == 0) stamp(4);
             tc_fence_after();
             const uint32_t a_hi = tmem_base + TMEM_A + s * (2 * BK), a_lo = a_hi + BK;
             const uint32_t b_hi = sbase + s * STAGE_BYTES + A_BYTES, b_lo = b_hi + B_BYTES;
@@ -180,6 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
           umma_commit(pfull(pb));  // partial accumulator complete
         }
       }
+      stamp(5);
     }
     __syncwarp();
   } else if (warp < 4) {
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
         const int s = it % RAW_STAGES;
         const uint32_t sa = sbase + s * STAGE_BYTES;
         mbar_wait(full(s), (it / RAW_STAGES) & 1);
+        if (it == 0 && threadIdx.x == 128) stamp(3);
         uint32_t h[32], w[32];
         if (!A_MN) {
           // K-major raw tile: row r = 128 bytes, 16-byte chunk c stored at chunk (c ^ (r & 7))
@@ -286,6 +296,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
         }
         tc_fence_before();
         mbar_arrive(pempty(pb));  // partial drained: the MMA warp may overwrite it
+        if (threadIdx.x == 256) stamp(6);
       }
       const int m_base = mb * BM + q * 32;
       if (m_base >= p.M) continue;  // warp-uniform
@@ -373,9 +384,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
       }
     }
   }
+  if (threadIdx.x == 256) stamp(7);
   if (warp >= 8 && lane == 0) bulk_wait_all();   // this warp's TMA stores have been performed
+  if (threadIdx.x == 256) stamp(8);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(9);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -438,6 +452,24 @@ template <bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tg,
            const GemmParams& p, int grid, cudaStream_t s) {
   NB_SET_SMEM_ONCE((k_gemm_tc<A_MN, B_MN>), SMEM_BYTES);
+  static const int timing = [] { const char* e = getenv("NEMO_B200_GEMM_TIMING"); return e ? atoi(e) : 0; }();
+  if (timing) {   // debug: one launch, synchronise, print CTA 0's timeline (cycles since kernel entry)
+    static unsigned long long* dbg = nullptr;
+    if (!dbg) NB_CUDA(cudaMalloc(&dbg, 16 * sizeof(unsigned long long)));
+    NB_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), s));
+    GemmParams q = p;
+    q.dbg = dbg;
+    k_gemm_tc<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, tc, tg, q);
+    NB_CUDA(cudaStreamSynchronize(s));
+    unsigned long long h[16];
+    NB_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    static const char* names[10] = {"entry", "setup done", "first TMA", "first full (A conv)", "first MMA", "last MMA issued",
+                                    "last partial drained", "epilogue issued", "stores performed", "all warps done"};
+    fprintf(stderr, "[gemm_tc timing] M=%d N=%d K=%d grid=%d splits=%d flush=%d:", p.M, p.N, p.K, grid, p.splits, p.flush);
+    for (int i = 1; i < 10; ++i) fprintf(stderr, "  %s %lld", names[i], h[i] ? (long long)(h[i] - h[0]) : -1LL);
+    fprintf(stderr, "\n");
+    return 0;
+  }
   k_gemm_tc<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, tc, tg, p);
   NB_LAUNCH_CHECK("gemm_tc");
 }
@@ -459,7 +491,7 @@ int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, 
             int force_splits, cudaStream_t s) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.act = act; p.ldg = ldg; p.accumulate = accumulate;
-  p.gslope = gslope; p.bias = bias; p.gate = gate; p.C = C;
+  p.gslope = gslope; p.bias = bias; p.gate = gate; p.C = C; p.dbg = nullptr;
   p.mtiles = cdiv(M, BM);
   p.ntiles = cdiv(N, BN);
   p.kblocks = cdiv(K, BK);

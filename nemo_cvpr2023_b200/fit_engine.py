@@ -187,6 +187,24 @@ def fold_vposer(sd, device):
                 Wd5=f(g('decoder_net.5.weight')), bd5=f(g('decoder_net.5.bias')))
 
 
+_NVTX = bool(int(__import__('os').environ.get('NEMO_B200_NVTX', '0')))
+
+
+class _Range:
+    """NVTX range around a phase of the step (NEMO_B200_NVTX=1): shows up in nsys / ncu --nvtx timelines."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+
+
 def _on_device(fn):
     """Run an engine method with the engine's device current (streams, events and the library's per-device state
     are created against the current device)."""
@@ -485,8 +503,9 @@ class FitEngine:
             w['raw'].copy_(phases)
         w['zbuf'].zero_()
         use_noise = self.version >= 3 and self.training and a.code_noise > 0 and self.Cc > 0
-        self._motion_forward(w, N, vi, w['raw'], use_noise)
-        self._shape(w)
+        with _Range('nemo.motion_forward'):
+            self._motion_forward(w, N, vi, w['raw'], use_noise)
+            self._shape(w)
         full = mode == 'step'
         need_2d = mode in ('step', 'opt_cam', 'cam_fit')
         mode_id = KP_LOSSES.index(a.loss)
@@ -616,7 +635,8 @@ class FitEngine:
             lib.rot6d_bwd(w['Y'], LDY, dR, 216, w['dY'], LDY, 24, 0, N * 24)
             # translation columns, pad column and the phase-0 row of dY (trans - trans_0, :3755-3766) in one launch
             lib.dy_tail(w['dtr'] if need_2d else None, w['dY'], LDY, N)
-            self._motion_backward(w, N, vi)
+            with _Range('nemo.motion_backward'):
+                self._motion_backward(w, N, vi)
             if w_inst:
                 self.g_inst.gviews['learned_instance_code'].add_(
                     self.g_inst.views['learned_instance_code'], alpha=ls * 2.0 * w_inst / (self.V * self.Cc))
@@ -733,7 +753,8 @@ class FitEngine:
             segs += g.segments(skip_lag)
         if not hasattr(self, '_adam_ticket'):
             self._adam_ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        adam_multi(segs, self._adam_ticket)
+        with _Range('nemo.adam'):
+            adam_multi(segs, self._adam_ticket)
 
     # ------------------------------------------------------------------ read-backs
     def loss_dict(self, w, norm):

@@ -339,6 +339,37 @@ class MultiViewModel(nn.Module):
         out['view_idx'], out['frame_idx'] = view_idx, frame_idx
         return out
 
+    def get_preds_given_phases_and_view(self, view_idx, input_phases, add_trans=True, phases=None):
+        """:3733-3781 / :3911-3956 / :4010-4058: the motion field evaluated at ALREADY WARPED phases `input_phases` (N,1)
+        for the instances `view_idx` -> (vertices (N,6890,3), joints (N,49,3), poses (N,69), orient 6D (N,6),
+        orient axis-angle (N,3), trans (N,3)).  Runs on the autograd ops (RBF, Linear, rot6d, rotmat->aa, SMPL), so
+        like the reference's it can be differentiated; the fit itself goes through the fused engine."""
+        a, dev = self.args, self.engine.dev
+        view_idx = self._idx(view_idx).to(dev)
+        x = torch.as_tensor(input_phases, dtype=torch.float32, device=dev).reshape(-1, 1)
+        n = x.shape[0]
+        has_rbf = self.VERSION >= 2 and a.phase_rbf_dim > 0
+        feats = self.phase_rbf(x) if has_rbf else x
+        if a.instance_code_size > 0:
+            code = self.learned_instance_code[view_idx]
+            if self.VERSION >= 3 and self.training and a.code_noise > 0:   # :3921-3923
+                code = code + a.code_noise * torch.randn_like(code)
+            feats = torch.cat([feats, code], 1)
+        pose_dict, orient_dict, trans = self.learned_motion(feats.contiguous())
+        out = self._get_smpl_given_poses(pose_dict['rotmat'].contiguous(), orient_dict['rot6d'].contiguous(), 'rotmat')
+        zero = torch.zeros(1, 1, device=dev)
+        inp0 = torch.cat([self.phase_rbf(zero) if has_rbf else zero,
+                          torch.zeros(1, a.instance_code_size, device=dev)], 1)
+        trans_0 = self.learned_motion(inp0.contiguous())[-1]
+        if not getattr(self, 'start_global_traj_anywhere', False):
+            trans = trans - trans_0
+        v, j = out.vertices, out.joints
+        if add_trans:
+            if getattr(self, 'detach_articulation', False):
+                v, j = v.detach(), j.detach()
+            v, j = v + trans.unsqueeze(1), j + trans.unsqueeze(1)
+        return v, j, pose_dict['pose'], orient_dict['rot6d'], orient_dict['pose'], trans
+
     def get_preds(self, add_trans=True):
         """:2986-3003: one get_preds_batch per view, stacked to (V, F, ...)."""
         all_preds = defaultdict(list)
@@ -569,7 +600,12 @@ class MultiViewModel(nn.Module):
                 o.sync_hyper()
             w, _ = e.step_graph(vi, fi, mode='warmup', which=[self.opt_motion._g, self.opt_phase._g], skip_lag=True)
             losses.append(w['acc'][2].clone())   # `acc` is a reused workspace slot
-        return [float(x) for x in torch.stack(losses).cpu()]
+        out = [float(x) for x in torch.stack(losses).cpu()]
+        # the reference stops on the first NaN gradient or collapsed pose (:3497-3508); here the loop never leaves the
+        # device, so the check happens once, on the loss trace and on the parameters the warm-up stepped
+        if not (np.isfinite(out).all() and bool(torch.isfinite(e.g_motion.p).all()) and bool(torch.isfinite(e.g_phase.p).all())):
+            raise FloatingPointError('nan gradient found during warm-up (reference: nemo/neural_motion_model.py:3497-3500)')
+        return out
 
     def opt_cam(self, cam_opt_steps=2000):
         """:2869-2906: Adam on the cameras only, first frame of every view, plain-mean reprojection loss."""

@@ -153,3 +153,24 @@ def test_v4_opt_cam_iteration_matches_oracle():
     torch.manual_seed(1)
     m.opt_cam(3)   # the loop itself: samples, detaches, steps every optimiser
     assert all(torch.isfinite(p).all() for p in m.engine.named_params().values())
+
+
+def test_get_preds_given_phases_and_view_matches_get_preds_batch():
+    """:3733-3781: the motion field at ALREADY WARPED phases.  Feeding it the warped phases of a batch must reproduce
+    `get_preds_batch` (fused engine) through the autograd ops: vertices, the 25 loss joints out of the 49, poses,
+    orientation, translation -- and it is differentiable like the reference's."""
+    args, orc, m, r = _pair()
+    vi, fi = torch.tensor(r.randint(0, 4, 40)), torch.tensor(r.randint(0, 12, 40))
+    ref = m.get_preds_batch(vi, fi)
+    warped = m.engine.ws(40)['warped'].clone()
+    v, j, poses, orient, orient_aa, trans = m.get_preds_given_phases_and_view(vi, warped.view(-1, 1))
+    assert v.shape == (40, 6890, 3) and j.shape == (40, 49, 3)
+    idx = [38] + list(range(1, 25))
+    assert float((v - ref['v']).abs().max()) < 2e-5 and float((j[:, idx] - ref['j']).abs().max()) < 2e-5
+    assert float((poses - ref['poses']).abs().max()) < 1e-5 and float((orient - ref['orient']).abs().max()) < 1e-5
+    assert float((trans - ref['trans']).abs().max()) < 1e-5 and float((orient_aa - ref['orient_aa']).abs().max()) < 1e-5
+    o = orc.get_preds_batch(vi, fi)
+    assert float((v.cpu() - o['v']).abs().max()) < 2e-5
+    ph = warped.view(-1, 1).clone().requires_grad_(True)
+    m.get_preds_given_phases_and_view(vi, ph)[1].sum().backward()
+    assert torch.isfinite(ph.grad).all() and float(ph.grad.abs().max()) > 0
