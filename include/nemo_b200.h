@@ -300,8 +300,9 @@ int nemo_b200_combine_losses(const float* terms, const float* weights, int n, fl
 /* Gradient rows of the (N+1, 147) MotionNet output beyond the 144 rot6d columns (the fit models subtract the phase-0
  * translation, trans - trans_0, nemo/neural_motion_model.py:3755-3766; row N of the MLP batch is that phase-0 sample):
  *   dY[n, 144:147] = dtrans[n],  dY[n, 147..ldy) = 0  (n < N);   dY[N, 0:144] = 0,  dY[N, 144:147] = -sum_n dtrans[n].
- * dtrans (N,3) may be NULL (= zeros).  Columns 0..143 of rows n < N belong to nemo_b200_rot6d_bwd. */
-int nemo_b200_dy_tail(const float* dtrans, float* dY, int ldy, int N, void* stream);
+ * dtrans (N,3) may be NULL (= zeros).  Columns 0..143 of rows n < N belong to nemo_b200_rot6d_bwd.
+ * scratch: 4 floats the caller has zeroed (column sums + a ticket; left dirty). */
+int nemo_b200_dy_tail(const float* dtrans, float* dY, int ldy, int N, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -708,12 +708,13 @@ __global__ void __launch_bounds__(256) k_gmm(const float* __restrict__ pose, int
                                              const float* __restrict__ prec, const float* __restrict__ nllw, int M,
                                              float* __restrict__ ll, float gscale, float* __restrict__ dpose, int ldd,
                                              int acc, int N) {
-  __shared__ float sP[GD * GDP];     // symmetrised precision of the current component, rows padded to 72
+  __shared__ __align__(16) float sP[GD * GDP];     // symmetrised precision of the current component, rows padded to 72
   __shared__ float sD[GDP][33];      // d[j][sample]
   __shared__ float sQ[8][32];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int n = blockIdx.x * 32 + lane;
   bool live = n < N;
+  for (int i = threadIdx.x; i < GD * (GDP - GD); i += 256) sP[(i / (GDP - GD)) * GDP + GD + i % (GDP - GD)] = 0.f;
   float x[GD];
 #pragma unroll
   for (int j = 0; j < GD; ++j) x[j] = live ? pose[(size_t)n * ldp + j] : 0.f;
@@ -727,9 +728,11 @@ __global__ void __launch_bounds__(256) k_gmm(const float* __restrict__ pose, int
       int a = i / GD, b = i % GD;
       sP[a * GDP + b] = 0.5f * (prec[((size_t)m * GD + a) * GD + b] + prec[((size_t)m * GD + b) * GD + a]);
     }
-    float d[GD];
+    float d[GDP];
 #pragma unroll
     for (int j = 0; j < GD; ++j) d[j] = x[j] - means[m * GD + j];
+#pragma unroll
+    for (int j = GD; j < GDP; ++j) d[j] = 0.f;
     if (w == 0) {
 #pragma unroll
       for (int j = 0; j < GD; ++j) sD[j][lane] = d[j];
@@ -741,9 +744,13 @@ __global__ void __launch_bounds__(256) k_gmm(const float* __restrict__ pose, int
       int i = w * 9 + r;
       float a = 0.f;
       if (i < GD) {
-        const float* row = sP + i * GDP;
+        // the row is a warp-wide broadcast: 16-byte loads quarter the LSU instructions that pace this kernel
+        const float4* row = reinterpret_cast<const float4*>(sP + i * GDP);
 #pragma unroll
-        for (int j = 0; j < GD; ++j) a += row[j] * d[j];
+        for (int j = 0; j < GDP / 4; ++j) {
+          const float4 p4 = row[j];
+          a += p4.x * d[4 * j] + p4.y * d[4 * j + 1] + p4.z * d[4 * j + 2] + p4.w * d[4 * j + 3];
+        }
         q += a * sD[i][lane];
       }
       y[r] = a;
@@ -933,11 +940,14 @@ extern "C" int nemo_b200_act_bwd(const float* dy, const float* y, float* out, si
   k_act_bwd<<<cdiv((long long)n, 256), 256, 0, S(stream)>>>(dy, y, out, n, act == 1 ? 0.f : 0.01f);
   NB_LAUNCH_CHECK("act_bwd");
 }
-// see nemo_b200_dy_tail in the header; one CTA: column sums of dtrans over the N rows by block reduction
-__global__ void __launch_bounds__(256) k_dy_tail(const float* __restrict__ dtr, float* __restrict__ dY, int ldy, int N) {
-  __shared__ float red[3][256];
+// see nemo_b200_dy_tail in the header.  Each CTA fills the tail columns of a slice of rows and adds its column sums of
+// dtrans to scratch[0..2]; the last CTA to finish (ticket in scratch[3]) writes the phase-0 row.
+__global__ void __launch_bounds__(256) k_dy_tail(const float* __restrict__ dtr, float* __restrict__ dY, int ldy, int N,
+                                                 float* __restrict__ scratch) {
+  __shared__ float red[3][8];
+  __shared__ int last;
   float s[3] = {0.f, 0.f, 0.f};
-  for (int n = threadIdx.x; n < N; n += 256) {
+  for (int n = blockIdx.x * 256 + threadIdx.x; n < N; n += gridDim.x * 256) {
     float* row = dY + (size_t)n * ldy;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -948,21 +958,30 @@ __global__ void __launch_bounds__(256) k_dy_tail(const float* __restrict__ dtr, 
     for (int c = 147; c < ldy; ++c) row[c] = 0.f;
   }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) red[c][threadIdx.x] = s[c];
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) red[c][threadIdx.x] += red[c][threadIdx.x + o];
-    }
-    __syncthreads();
+  for (int c = 0; c < 3; ++c) {
+    const float v = warp_sum(s[c]);
+    if ((threadIdx.x & 31) == 0) red[c][threadIdx.x >> 5] = v;
   }
-  float* last = dY + (size_t)N * ldy;
-  for (int c = threadIdx.x; c < ldy; c += 256) last[c] = (c >= 144 && c < 147) ? -red[c - 144][0] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    atomicAdd(scratch + threadIdx.x, v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<int*>(scratch + 3), 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float* lastrow = dY + (size_t)N * ldy;
+  for (int c = threadIdx.x; c < ldy; c += 256)
+    lastrow[c] = (c >= 144 && c < 147) ? -__ldcg(scratch + (c - 144)) : 0.f;
 }
-extern "C" int nemo_b200_dy_tail(const float* dtrans, float* dY, int ldy, int N, void* stream) {
-  NB_REQUIRE(dY && ldy >= 147 && N >= 0, "dy_tail: bad args");
-  k_dy_tail<<<1, 256, 0, S(stream)>>>(dtrans, dY, ldy, N);
+extern "C" int nemo_b200_dy_tail(const float* dtrans, float* dY, int ldy, int N, float* scratch, void* stream) {
+  NB_REQUIRE(dY && scratch && ldy >= 147 && N >= 0, "dy_tail: bad args");
+  k_dy_tail<<<max(1, min(cdiv(N, 256), 64)), 256, 0, S(stream)>>>(dtrans, dY, ldy, N, scratch);
   NB_LAUNCH_CHECK("dy_tail");
 }
 __global__ void k_combine(const float* __restrict__ t, const float* __restrict__ w, int n, float* __restrict__ out) {

@@ -857,6 +857,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_skin_tc_bwd(const SkinBwdArg
   }
 }
 
+}  // namespace
+
+namespace nb {
+int skin_fwd2(const float* A, const float* PO, const float* base, const float* Wt, float* V, int N, cudaStream_t s);
+int skin_l1_fwd2(const float* A_a, const float* PO_a, const float* A_b, const float* PO_b, const float* base,
+                 const float* Wt, uint32_t* signs, float* l1_sum, int N, cudaStream_t s);
+void skin_chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int max_chunks, int& groups_per_chunk,
+                   int& nchunks);
+}  // namespace nb
+
+namespace {
+static int fwd_generation() {
+  static const int g = [] { const char* e = getenv("NEMO_B200_SKIN_FWD"); return e ? atoi(e) : 2; }();
+  return g;
+}
+
 // Frame groups per CTA.  Every CTA pays a set-up (W operands into shared / tensor memory) worth `setup` groups, and
 // the grid runs in waves over 148 x ctas_per_sm slots: pick the chunk count that minimises waves x (groups + set-up).
 void chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int max_chunks, int& groups_per_chunk,
@@ -877,6 +893,12 @@ void chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int ma
   groups_per_chunk = cdiv(groups, best);
   nchunks = cdiv(groups, groups_per_chunk);
 }
+}  // namespace
+void nb::skin_chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int max_chunks, int& groups_per_chunk,
+                       int& nchunks) {
+  chunking(N, frames_per_group, ctas_per_sm, setup, max_chunks, groups_per_chunk, nchunks);
+}
+namespace {
 
 template <int MODE>
 int launch_fwd(const SkinArgs& a, cudaStream_t s) {
@@ -934,6 +956,7 @@ extern "C" int nemo_b200_skin_fwd(const float* A, const float* PO, const float* 
                                   void* stream) {
   if (N == 0) return 0;
   NB_REQUIRE(A && PO && base && Wt && V && N >= 0, "skin_fwd: bad args");
+  if (fwd_generation() >= 2) return nb::skin_fwd2(A, PO, base, Wt, V, N, S(stream));
   SkinArgs a{};
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.V = V; a.N = N;
   chunking(N, FB, 2, 2.0, 32, a.groups_per_chunk, a.nchunks);
@@ -945,6 +968,7 @@ extern "C" int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const 
                                      void* stream) {
   if (N == 0) return 0;
   NB_REQUIRE(A_a && PO_a && A_b && PO_b && base && Wt && signs && l1_sum && N >= 0, "skin_l1_fwd: bad args");
+  if (fwd_generation() >= 2) return nb::skin_l1_fwd2(A_a, PO_a, A_b, PO_b, base, Wt, signs, l1_sum, N, S(stream));
   SkinArgs a{};
   a.A = A_a; a.PO = PO_a; a.A2 = A_b; a.PO2 = PO_b; a.base = base; a.Wt = Wt; a.signs = signs; a.l1_sum = l1_sum;
   a.N = N;

@@ -328,7 +328,7 @@ class FitEngine:
 
     def _dp_bucket(self, name):
         """all-reduce one finished range of the shared gradient on the communication stream"""
-        if self.world <= 1 or not self.dp_overlap:
+        if self.world <= 1 or not self.dp_overlap or self.dp_defer:
             return
         import torch.distributed as dist
         lo, hi = self._dp_buckets[name]
@@ -342,9 +342,9 @@ class FitEngine:
             self._comm.wait_event(ev)
             self._dp_handles.append(dist.all_reduce(self.g_motion.g[lo:hi], group=self.dp_group, async_op=True))
 
-    def _dp_finish(self):
+    def _dp_finish(self, plain=False):
         import torch.distributed as dist
-        if self.dp_overlap:
+        if self.dp_overlap and not plain:
             self._dp_bucket('tail')
         else:
             dist.all_reduce(self.g_motion.g, group=self.dp_group)
@@ -422,8 +422,9 @@ class FitEngine:
         )
         # per-step accumulators (loss terms, per-view sums, camera gradient sums): one buffer, one fill per step
         V = self.V
-        w['zbuf'] = z(8 + 14 * V)
-        w['acc'], w['view_acc'], w['dcam'] = w['zbuf'][:8], w['zbuf'][8:8 + 2 * V].view(V, 2), w['zbuf'][8 + 2 * V:].view(V, 12)
+        w['zbuf'] = z(8 + 14 * V + 4)
+        w['acc'], w['view_acc'] = w['zbuf'][:8], w['zbuf'][8:8 + 2 * V].view(V, 2)
+        w['dcam'], w['dyscr'] = w['zbuf'][8 + 2 * V:8 + 14 * V].view(V, 12), w['zbuf'][8 + 14 * V:]
         self._ws[N] = w
         return w
 
@@ -634,7 +635,7 @@ class FitEngine:
             lib.rotmat2aa_bwd(w['R'], 9, w['d_aa'], 3, dR, 9, 1, 1, N * 24, 1)
             lib.rot6d_bwd(w['Y'], LDY, dR, 216, w['dY'], LDY, 24, 0, N * 24)
             # translation columns, pad column and the phase-0 row of dY (trans - trans_0, :3755-3766) in one launch
-            lib.dy_tail(w['dtr'] if need_2d else None, w['dY'], LDY, N)
+            lib.dy_tail(w['dtr'] if need_2d else None, w['dY'], LDY, N, w['dyscr'])
             with _Range('nemo.motion_backward'):
                 self._motion_backward(w, N, vi)
             if w_inst:
@@ -710,8 +711,10 @@ class FitEngine:
         cost that separates the end-to-end rate from the device-timed one.  The first call with a new key (batch size,
         mode, training flag, optimiser hyper-parameters -- the learning rates are baked into the launch parameters, a
         plateau scheduler that changes one simply causes a re-capture) runs eagerly, the second captures, later ones
-        replay.  The indices are copied into their fixed workspace slots outside the graph.  Not used under data
-        parallelism (NCCL calls stay eager) or when per-entry-point profiling is on."""
+        replay.  The indices are copied into their fixed workspace slots outside the graph.  Under data parallelism NCCL
+        stays outside the graphs: graph 1 = forward + backward, ONE eager all-reduce of the shared gradient, graph 2 = the
+        optimisers (the bucketed, overlapped all-reduce belongs to the eager `forward_backward`).  Not used when
+        per-entry-point profiling is on."""
         N = int(view_idx.shape[0])
         w = self.ws(N)
         w['vi'].copy_(view_idx, non_blocking=True)
@@ -720,18 +723,37 @@ class FitEngine:
         key = (N, mode, bool(detach_pose), bool(self.training), bool(skip_lag), bool(self.compute_betas_grad),
                tuple((id(g), g.lr, g.wd, g.betas, g.eps, g.decoupled) for g in groups))
 
+        dp = self.world > 1
+
         def body():
-            out = self.forward_backward(w['vi'], w['fi'], update=True, mode=mode, detach_pose=detach_pose,
-                                        _indices_loaded=True)
-            self.optimizer_step(groups, skip_lag=skip_lag)
+            # data parallel: the graph stops before the all-reduce (NCCL stays OUTSIDE the captured graphs: one eager
+            # collective between the two replays; a second graph holds the optimisers)
+            saved = self.dp_defer
+            self.dp_defer = self.dp_defer or dp
+            try:
+                out = self.forward_backward(w['vi'], w['fi'], update=True, mode=mode, detach_pose=detach_pose,
+                                            _indices_loaded=True)
+            finally:
+                self.dp_defer = saved
+            if not dp:
+                self.optimizer_step(groups, skip_lag=skip_lag)
             return out
 
-        if self.world > 1 or lib.profile is not None or not self.use_graph:
-            return body()
+        def tail():
+            if dp and not self.dp_defer:
+                self._dp_finish(plain=True)
+                self._adam_graph(groups, skip_lag, key)
+
+        if lib.profile is not None or not self.use_graph:
+            out = body()
+            tail()
+            return out
         ent = self._graphs.get(key)
         if ent is None:                       # first sight of this key: the eager run doubles as the warm-up
             self._graphs[key] = 'warm'
-            return body()
+            out = body()
+            tail()
+            return out
         if ent == 'warm':
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.dev)
@@ -739,7 +761,23 @@ class FitEngine:
                 out = body()
             ent = self._graphs[key] = (g, out)
         ent[0].replay()
+        tail()
         return ent[1]
+
+    def _adam_graph(self, groups, skip_lag, key):
+        """the optimisers of a data-parallel step as their own small graph (after the eager all-reduce)"""
+        k = ('adam',) + key
+        ent = self._graphs.get(k)
+        if ent is None or not self.use_graph:
+            self._graphs[k] = 'warm'
+            return self.optimizer_step(groups, skip_lag=skip_lag)
+        if ent == 'warm':
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(g):
+                self.optimizer_step(groups, skip_lag=skip_lag)
+            ent = self._graphs[k] = (g, None)
+        ent[0].replay()
 
     def drop_graphs(self, group):
         """forget the captured steps that reference `group`'s buffers"""

@@ -21,7 +21,7 @@ class MultiActionFit:
         self.dev = torch.device(device if device is not None else self.models[0].engine.dev)
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in self.models]
         self.world, self.group = 1, None
-        self._flat = None
+        self._flat, self._graphs = None, {}
 
     def enable_data_parallel(self, world_size, group=None, reduce_all=False):
         self.world, self.group = int(world_size), group
@@ -70,30 +70,63 @@ class MultiActionFit:
             self._allreduce_all()
         return outs
 
-    def train_step(self, view_idx, frame_idx):
-        """forward + backward + Adam of every action; one CUDA-graph launch per action on its own stream when the fit
-        runs on one GPU (the all-reduce of a data-parallel fit sits between backward and Adam, so that path is eager).
-        Returns the engines' (workspace, norm) pairs."""
-        if self.world > 1:
-            outs = self.forward_backward(view_idx, frame_idx, update=True)
-            self.optimizer_step()
-            return outs
+    def _fb_body(self):
+        """every action's forward + backward on its own stream (and, on one GPU, its Adam)"""
         cur = torch.cuda.current_stream(self.dev)
         fork = torch.cuda.Event()
         fork.record(cur)
         outs = []
-        for m, st, vi, fi in zip(self.models, self.streams, view_idx, frame_idx):
+        for m, st in zip(self.models, self.streams):
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 e = m.engine
+                w = e.ws(self._n)
                 e.training = m.training or m.VERSION >= 3
-                for o in m.optimizers:
-                    o.sync_hyper()
-                outs.append(e.step_graph(vi, fi, mode='step', which=[o._g for o in m.optimizers]))
+                outs.append(e.forward_backward(w['vi'], w['fi'], update=True, mode='step', _indices_loaded=True))
+                if self.world == 1:
+                    e.optimizer_step([o._g for o in m.optimizers])
                 e.training = False
             ev = torch.cuda.Event()
             ev.record(st)
             cur.wait_event(ev)
+        return outs
+
+    def _adam_body(self):
+        for m in self.models:
+            m.engine.optimizer_step([o._g for o in m.optimizers])
+
+    def _graphed(self, key, fn):
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = 'warm'
+            return fn()
+        if ent == 'warm':
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(g):
+                out = fn()
+            ent = self._graphs[key] = (g, out)
+        ent[0].replay()
+        return ent[1]
+
+    def train_step(self, view_idx, frame_idx):
+        """forward + backward + Adam of every action as ONE CUDA-graph launch: the actions' kernels sit on parallel
+        branches of the graph (one stream each at capture time).  Data parallel: graph 1 = every forward + backward, one
+        EAGER all-reduce over all actions' shared gradients (NCCL stays outside the graphs), graph 2 = every Adam.  First
+        call eager, second captures, later ones replay; the indices are copied into the engines' workspace slots outside
+        the graphs.  Returns the engines' (workspace, norm) pairs."""
+        self._n = int(view_idx[0].shape[0])
+        for m, vi, fi in zip(self.models, view_idx, frame_idx):
+            w = m.engine.ws(self._n)
+            w['vi'].copy_(vi, non_blocking=True)
+            w['fi'].copy_(fi, non_blocking=True)
+            for o in m.optimizers:
+                o.sync_hyper()
+        key = (self._n, tuple((g.lr, g.wd) for m in self.models for g in m.engine.groups()))
+        outs = self._graphed(('fb',) + key, self._fb_body)
+        if self.world > 1:
+            self._allreduce_all()
+            self._graphed(('adam',) + key, self._adam_body)
         return outs
 
     def optimizer_step(self):

@@ -39,11 +39,18 @@ def _problem(V):
 
 
 def _run(model, V, F):
+    """one step (eager, bucketed all-reduce overlapped with the backward: gradients and parameters are compared after
+    it), then two more -- the second call captures forward + backward and the optimisers into CUDA graphs around ONE
+    eager all-reduce, the third replays them; their losses are returned too"""
     vi, fi = torch.arange(V).repeat_interleave(F), torch.arange(F).repeat(V)
     ld, _ = model.step(vi, fi)
     g = {k: v.detach().cpu().numpy().copy() for k, v in model.engine.named_grads().items()}
     p = {k: v.detach().cpu().numpy().copy() for k, v in model.engine.named_params().items()}
-    return {k: float(v) for k, v in ld.items()}, g, p
+    out = {k: float(v) for k, v in ld.items()}
+    for i in (2, 3):
+        ld, _ = model.step(vi, fi)
+        out['total_loss_step%d' % i] = float(ld['total_loss'])
+    return out, g, p
 
 
 def _worker(rank, world, port, V, out_path):
@@ -76,6 +83,7 @@ def _local_name(k, views):
     return k
 
 
+@pytest.mark.timeout(240)
 @pytest.mark.parametrize('V', [8, 1])
 def test_two_ranks_equal_one_gpu(tmp_path, V):
     if torch.cuda.device_count() < 2:
@@ -89,12 +97,20 @@ def test_two_ranks_equal_one_gpu(tmp_path, V):
     del full
     torch.cuda.empty_cache()
     out_path = str(tmp_path / 'rank%d.npz')
-    mp.spawn(_worker, args=(world, 29600 + (os.getpid() % 300), V, out_path), nprocs=world, join=True)
+    ctx = mp.spawn(_worker, args=(world, 29600 + (os.getpid() % 300), V, out_path), nprocs=world, join=False)
+    import time
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > 180:   # a hung collective must not hold the GPU box: kill the ranks and fail
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail('data-parallel ranks did not finish within 180 s')
     for r in range(world):
         res = dict(np.load(out_path % r))
         views = list(res['views'])
         for k in ld:   # every rank reports the GLOBAL losses
-            assert_rel(res['loss.' + k], ld[k], 1e-5, 'rank %d %s' % (r, k))
+            # steps 2 / 3 (captured / replayed) run on parameters that one Adam step has moved by ~lr in every entry
+            assert_rel(res['loss.' + k], ld[k], 2e-3 if 'step' in k else 1e-5, 'rank %d %s' % (r, k))
         n = 0
         for k in g:
             if k == 'learned_betas':

@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_dp_nccl.py -m gpu -q -x > gpurun_out/pytest_nccl.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_nccl.log; tail -25 gpurun_out/pytest_nccl.log
+for c in 1 2 4; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --config $c --steps 20 --warmup 5 > gpurun_out/bench_n2_c$c.json 2> gpurun_out/bench_n2_c$c.err; cut -c1-200 gpurun_out/bench_n2_c$c.json; tail -4 gpurun_out/bench_n2_c$c.err | cut -c1-300
+done
+CUDA_VISIBLE_DEVICES=0 timeout 1200 python -m pytest tests -m gpu -q --deselect tests/test_gpu_dp_nccl.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -8 gpurun_out/pytest_gpu.log
+CUDA_VISIBLE_DEVICES=0 timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-200 gpurun_out/bench.json
