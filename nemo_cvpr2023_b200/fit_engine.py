@@ -302,6 +302,7 @@ class FitEngine:
         self.training = False
         self.world, self.loss_scale, self.dp_defer = 1, 1.0, False
         self.use_graph, self._graphs = True, {}
+        self.step_tick = 0        # forward_backward calls so far (lazily read step outputs check it)
 
     def enable_data_parallel(self, world_size, group=None, reduce_all=False, overlap=True):
         """Shard by video instance: this rank owns its views' cameras, instance codes and
@@ -320,6 +321,19 @@ class FitEngine:
         oh = off['learned_motion.rot_out.weight'][0]
         ot = off['phase_rbf.log_sigmas'][0] if self.D > 0 else self.g_motion.g.numel()
         self._dp_buckets = dict(head=(oh, ot), l4=(o4, oh), l2=(o2, o4), l0=(0, o2), tail=(ot, self.g_motion.g.numel()))
+
+    def track_info(self, info):
+        import weakref
+        self._pending_info = weakref.ref(info)
+
+    def _flush_info(self):
+        """the previous step's lazily read outputs, if somebody still holds them, are copied out of the workspace now"""
+        ref = getattr(self, '_pending_info', None)
+        if ref is not None:
+            self._pending_info = None
+            obj = ref()
+            if obj is not None:
+                obj.materialize()
 
     def set_frame_window(self, frame_lo, total_frames):
         """This engine holds frames [frame_lo, frame_lo + F) of sequences that are `total_frames` long (data-parallel
@@ -494,6 +508,9 @@ class FitEngine:
         N = int(view_idx.shape[0])
         w = self.ws(N)
         Np, h = N + 1, self.h
+        if not _indices_loaded:
+            self._flush_info()
+        self.step_tick += 1
         if not _indices_loaded:
             w['vi'].copy_(view_idx, non_blocking=True)
             w['fi'].copy_(frame_idx, non_blocking=True)
@@ -717,6 +734,7 @@ class FitEngine:
         per-entry-point profiling is on."""
         N = int(view_idx.shape[0])
         w = self.ws(N)
+        self._flush_info()
         w['vi'].copy_(view_idx, non_blocking=True)
         w['fi'].copy_(frame_idx, non_blocking=True)
         groups = which or self.groups()
@@ -761,6 +779,7 @@ class FitEngine:
                 out = body()
             ent = self._graphs[key] = (g, out)
         ent[0].replay()
+        self.step_tick += 1
         tail()
         return ent[1]
 
@@ -819,6 +838,7 @@ class FitEngine:
         C = self.C_
         N = int(view_idx.shape[0])
         w = self.ws(N)
+        self._flush_info()
         w['vi'].copy_(view_idx)
         if phases is None:
             w['fi'].copy_(frame_idx)

@@ -14,6 +14,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .nemo.neural_motion_model import _StepInfo
+
 
 class MultiActionFit:
     def __init__(self, models, device=None):
@@ -118,6 +120,8 @@ class MultiActionFit:
         self._n = int(view_idx[0].shape[0])
         for m, vi, fi in zip(self.models, view_idx, frame_idx):
             w = m.engine.ws(self._n)
+            m.engine._flush_info()
+            m.engine.step_tick += 1
             w['vi'].copy_(vi, non_blocking=True)
             w['fi'].copy_(fi, non_blocking=True)
             for o in m.optimizers:
@@ -142,8 +146,7 @@ class MultiActionFit:
         res = []
         for m, (w, norm), row in zip(self.models, outs, host):
             ld = m.engine.loss_dict_from_host(row, norm)
-            res.append(({k: ld[k] for k in m._LOSS_KEYS},
-                        {'view_idx': w['vi'], 'frame_idx': w['fi'], 'loss_all': w['loss_all']}))
+            res.append(({k: ld[k] for k in m._LOSS_KEYS}, _StepInfo(m.engine, w, m.points2d_gt_all)))
         return res
 
     def losses_packed(self, outs):

@@ -188,6 +188,56 @@ class FusedAdam(torch.optim.Optimizer):
         self.sync_hyper()
 
 
+class _StepInfo(dict):
+    """`info_dict` of `step` (view_idx, frame_idx, loss_all (N,25,2), points2d_gt (N,25,3)).  The tensors live in the
+    engine's reused workspace; an entry is copied out of it when it is first read (the fit loop of the reference reads
+    them only when it logs, scripts/learned_multi_view_recon_nn.py:247-308), which keeps four copy kernels out of an
+    iteration whose info_dict is dropped.  An info_dict that is still referenced when the model steps again is filled
+    in just before the workspace is overwritten (`FitEngine._flush_info`), so it never shows a later step's data."""
+    _LAZY = ('view_idx', 'frame_idx', 'loss_all', 'points2d_gt')
+
+    def __init__(self, engine, w, gt_all):
+        super().__init__()
+        self._e, self._w, self._gt, self._tick = engine, w, gt_all, engine.step_tick
+        engine.track_info(self)
+
+    def materialize(self):
+        for k in self._LAZY:
+            self[k]
+
+    def __missing__(self, k):
+        if k not in self._LAZY:
+            raise KeyError(k)
+        if self._e.step_tick != self._tick:
+            raise RuntimeError('info_dict[%r] of an earlier step was first read after the model stepped again' % k)
+        w = self._w
+        v = {'view_idx': lambda: w['vi'].clone(), 'frame_idx': lambda: w['fi'].clone(),
+             'loss_all': lambda: w['loss_all'].clone(), 'points2d_gt': lambda: self._gt[w['vi'], w['fi']]}[k]()
+        self[k] = v
+        return v
+
+    def __contains__(self, k):
+        return k in self._LAZY or dict.__contains__(self, k)
+
+    def keys(self):
+        return list(self._LAZY)
+
+    def __iter__(self):
+        return iter(self._LAZY)
+
+    def __len__(self):
+        return len(self._LAZY)
+
+    def items(self):
+        return [(k, self[k]) for k in self._LAZY]
+
+    def values(self):
+        return [self[k] for k in self._LAZY]
+
+    def get(self, k, default=None):
+        return self[k] if k in self._LAZY else default
+
+
 class MultiViewModel(nn.Module):
     """:151-255 + the fit-path methods (:2758-3124).  Extra keyword arguments replace the licensed files the
     reference loads from `software/`: `smpl_arrays`, `vposer_state`, `gmm` (default: seeded synthetic
@@ -562,8 +612,7 @@ class MultiViewModel(nn.Module):
         if update and self.args.lr_factor < 1:
             for s in self.schedulers:
                 s.step(float(ld['total_loss']))
-        info_dict = {'view_idx': w['vi'].clone(), 'frame_idx': w['fi'].clone(), 'loss_all': w['loss_all'].clone(),
-                     'points2d_gt': self.points2d_gt_all[w['vi'], w['fi']]}
+        info_dict = _StepInfo(e, w, self.points2d_gt_all)
         self.training = False
         e.training = False
         return loss_dict, info_dict
