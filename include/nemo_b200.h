@@ -49,14 +49,23 @@ int nemo_b200_gemm(const float* A, const float* B, const float* bias, float* C,
                    int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                    int act, const float* gate, int ldg, float gate_slope, int accumulate,
                    void* stream);
-/* nemo_b200_gemm dispatches: 16-byte aligned operands with lda, ldb multiples of 4 and M*N*K >= 2e6 run on the
- * tensor-core kernel, everything else on the CUDA-core kernel. */
+/* nemo_b200_gemm dispatches: 16-byte aligned operands with lda, ldb multiples of 4 and M*N*K >= 2e6 run on a
+ * tensor-core kernel, everything else on the CUDA-core kernel.  Row padding: when C is 16-byte addressable (aligned,
+ * ldc % 4 == 0) and N % 4 != 0 with ldc - N < 4, the tensor-core kernels write the tile through 16-byte TMA stores and the
+ * up to three PADDING floats [N, ldc) of each row receive zeros. */
 /* same contract, always on the tcgen05 3xTF32 tensor-core kernel (TMA-fed; A and B must be 16-byte aligned
  * with lda, ldb multiples of 4).  splits > 0 forces the split-K factor (act must be 0), 0 = heuristic. */
 int nemo_b200_gemm_tc(const float* A, const float* B, const float* bias, float* C,
                       int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                       int act, const float* gate, int ldg, float gate_slope, int accumulate,
                       int splits, void* stream);
+/* same contract on the second-generation tensor-core kernel (128 x 256 x 16 tiles, N = 256 MMAs, TMA epilogue only:
+ * C and gate must additionally be 16-byte aligned with ldc, ldg multiples of 4, and N % 4 == 0 or ldc - N < 4).  nemo_b200_gemm picks between the two
+ * by the estimated tensor-pipe time of the shape. */
+int nemo_b200_gemm_tc2(const float* A, const float* B, const float* bias, float* C,
+                       int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                       int act, const float* gate, int ldg, float gate_slope, int accumulate,
+                       int splits, void* stream);
 /* same contract, always on the CUDA cores (fp32 FMA); the cross-check of the tensor-core path */
 int nemo_b200_gemm_simt(const float* A, const float* B, const float* bias, float* C,
                         int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,

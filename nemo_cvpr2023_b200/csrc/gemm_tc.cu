@@ -505,7 +505,11 @@ int gemm_tc(const float* A, const float* B, const float* bias, float* C, int M, 
   { const int kpu = cdiv(p.kblocks, splits); p.flush = kpu <= 8 ? 8 : 4; }
   static const int flush_env = [] { const char* e = getenv("NEMO_B200_GEMM_FLUSH"); return e ? atoi(e) : 0; }();
   if (flush_env > 0) p.flush = flush_env;   // experiment knob: k-blocks per TMEM partial
-  p.vec = (((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && (!gate || (((uintptr_t)gate & 15) == 0 && (ldg & 3) == 0))) ? 1 : 0;
+  // TMA epilogue: C (and the gate) 16-byte addressable.  TMA stores move whole 16-byte chunks: with N % 4 != 0 the up to
+  // three floats [N, N rounded up to 4) of every row receive zeros (+= 0 under reduce-add), so the path is taken only
+  // when those floats are the row's trailing padding (ldc - N < 4).
+  p.vec = (((uintptr_t)C & 15) == 0 && (ldc & 3) == 0 && ((N & 3) == 0 || ldc - N < 4) &&
+           (!gate || (((uintptr_t)gate & 15) == 0 && (ldg & 3) == 0))) ? 1 : 0;
   if (splits > 1 && !accumulate)
     NB_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
   CUtensorMap ta, tb;

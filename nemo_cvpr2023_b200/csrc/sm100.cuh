@@ -48,10 +48,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Blocks until the phase with the given parity has completed.  A wait that never completes (a protocol
-// bug) traps after ~2^24 polls instead of hanging the device.
+// Blocks until the phase with the given parity has completed.  A wait that never completes (a protocol bug) traps
+// after ~2 s of SM clock instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, polls = 0;
+  uint32_t done = 0, t0 = 0, armed = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -64,7 +64,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #ifdef NB_MBAR_SLEEP
     __nanosleep(NB_MBAR_SLEEP);
 #endif
-    if (++polls > (1u << 24)) __trap();
+    const uint32_t now = (uint32_t)clock();
+    if (!armed) { t0 = now; armed = 1; }
+    else if (now - t0 > 3500000000u) __trap();
   }
 }
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA, tcgen05.mma operand reads)
@@ -148,7 +150,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 //   K-major operand, 128-byte swizzle, 32 fp32 of K per row:   LBO unused, SBO = 1024 (8 rows), layout 2
 //   MN-major fp32 operand, 128-byte swizzle with 32-byte atoms: LBO = stride between 32-wide MN blocks,
 //                                                               SBO = 512 (4 k-rows), layout 1
-constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1, LAYOUT_SW64 = 4;
+// warp-specialised register reallocation: all four warps of a warpgroup execute it (counts are multiples of 8)
+template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout) {
   uint64_t d = 0;
@@ -201,6 +206,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// registers -> TMEM: this thread's lane, 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -147,3 +147,69 @@ def test_gemm_tc_tma_epilogue(lib):
     lib.gemm_tc(G(A2), G(B2), None, C, M2, N2, K2, 208, N2, N2, 0, 0, 0, None, 0, 0.0, 0, 0)
     ref = A2[:, :K2].astype(np.float64) @ B2.astype(np.float64)
     assert np.abs(npy(C) - ref).max() / np.abs(ref).max() < 4e-6
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_gemm_tc2_layouts(lib, ta, tb):
+    """second-generation kernel (128 x 256 x 16 tiles, 64-byte swizzled K-major rows): every layout, ragged tails"""
+    r = np.random.RandomState(31 + 2 * ta + tb)
+    for (M, N, K) in [(128, 256, 16), (4097, 1000, 1000), (300, 207, 6912), (513, 1000, 104), (1000, 1000, 4097),
+                      (2048, 2 * 3456, 207), (77, 300, 1000), (33, 9, 40)]:
+        A = r.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+        B = r.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+        ref = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+        Ad, lda = pad_ld(A)
+        Bd, ldb = pad_ld(B)
+        # N % 4 == 0: C may sit inside a wider matrix, its neighbours stay untouched; else only trailing row padding
+        ldc = N + 8 if N % 4 == 0 else (N + 3) // 4 * 4
+        C = torch.full((M + 1, ldc), 7.0, device=DEV)
+        lib.gemm_tc2(Ad, Bd, None, C, M, N, K, lda, ldb, ldc, ta, tb, 0, None, 0, 0.0, 0, 1)
+        torch.cuda.synchronize()
+        err = np.abs(npy(C)[:M, :N] - ref).max() / np.abs(ref).max()
+        assert err < 4e-6, 'gemm_tc2 ta=%d tb=%d %s: rel-max err %.3e' % (ta, tb, (M, N, K), err)
+        assert float((C[M:] - 7.0).abs().max()) == 0.0
+        if N % 4 == 0:
+            assert float((C[:, N:] - 7.0).abs().max()) == 0.0
+
+
+def test_gemm_tc2_epilogues_and_splitk(lib):
+    r = np.random.RandomState(41)
+    M, N, K = 1030, 1000, 520
+    A = r.standard_normal((M, K)).astype(np.float32)
+    B = r.standard_normal((N, K)).astype(np.float32)
+    bias = r.standard_normal(N).astype(np.float32)
+    gate = r.standard_normal((M, N)).astype(np.float32)
+    C0 = r.standard_normal((M, 1004)).astype(np.float32)
+    acc = A.astype(np.float64) @ B.T.astype(np.float64)
+    Ad, Bd, Gd = G(A), G(B), G(gate)
+    scale = np.abs(acc).max()
+    C = torch.full((M, N), 7.0, device=DEV)
+    lib.gemm_tc2(Ad, Bd, G(bias), C, M, N, K, K, K, N, 0, 1, 1, None, 0, 0.0, 0, 1)
+    assert np.abs(npy(C) - np.maximum(acc + bias, 0)).max() / scale < 4e-6
+    lib.gemm_tc2(Ad, Bd, G(bias), C, M, N, K, K, K, N, 0, 1, 2, None, 0, 0.0, 0, 1)
+    ref = acc + bias
+    assert np.abs(npy(C) - np.where(ref > 0, ref, 0.01 * ref)).max() / scale < 4e-6
+    Cs = G(C0)
+    lib.gemm_tc2(Ad, Bd, None, Cs, M, N, K, K, K, 1004, 0, 1, 0, Gd, N, 0.0, 0, 1)
+    ref = C0.astype(np.float64).copy()
+    ref[:, :N] = acc * (gate > 0)
+    assert np.abs(npy(Cs) - ref).max() / scale < 4e-6
+    for splits in (1, 3):
+        Cs = G(C0)
+        lib.gemm_tc2(Ad, Bd, None, Cs, M, N, K, K, K, 1004, 0, 1, 0, Gd, N, 0.01, 1, splits)
+        ref = C0.astype(np.float64).copy()
+        ref[:, :N] += acc * np.where(gate > 0, 1.0, 0.01)
+        assert np.abs(npy(Cs) - ref).max() / scale < 4e-6, 'splits=%d' % splits
+    Cs = G(C0)
+    lib.gemm_tc2(Ad, Bd, G(bias), Cs, M, N, K, K, K, 1004, 0, 1, 0, None, 0, 0.0, 0, 4)
+    ref = C0.astype(np.float64).copy()
+    ref[:, :N] = acc + bias
+    assert np.abs(npy(Cs) - ref).max() / scale < 4e-6
+    # heuristic split-K (dgrad-like: one tile column, deep K) and many tiles per CTA (pose-blend forward)
+    M2, N2, K2 = 2048, 207, 20736
+    A2 = (0.05 * r.standard_normal((M2, K2))).astype(np.float32)
+    B2 = r.standard_normal((N2, K2)).astype(np.float32)
+    C = torch.empty(M2, 208, device=DEV)
+    lib.gemm_tc2(G(A2), G(B2), None, C, M2, N2, K2, K2, K2, 208, 0, 1, 0, None, 0, 0.0, 0, 0)
+    ref = A2.astype(np.float64) @ B2.T.astype(np.float64)
+    assert np.abs(npy(C)[:, :N2] - ref).max() / np.abs(ref).max() < 4e-6
