@@ -119,6 +119,12 @@ int nemo_b200_pose_chain_fwd(const float* R, const float* aa, int lda, int kind,
 int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents,
                         const float* dA, const float* dAt, const float* dJP, float* dR, float* dJ, int N,
                         void* stream);
+/* chain_bwd + the backward of the pose feature: dF (N, ldf >= 207), the gradient of (R[1:] - I) -- what the dgrad of the
+ * pose-blend GEMM produces, written to its own 16-byte aligned rows so that GEMM runs with the TMA epilogue -- is added
+ * into dR[:, 1:].  dF may be NULL. */
+int nemo_b200_chain_bwd2(const float* R, const float* J, int j_stride, const int* parents,
+                         const float* dA, const float* dAt, const float* dJP, const float* dF, int ldf,
+                         float* dR, float* dJ, int N, void* stream);
 
 /* ---------------------------------------------------------------- skinning (K7)
  * lbs.py:236-252 (v_posed, T = W.A, v = T.[v_posed;1]), fused; no per-vertex intermediate is written.

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(CW * 32) k_chain_fwd(const float* __restrict__
 __global__ void __launch_bounds__(CW * 32) k_chain_bwd(const float* __restrict__ R, const float* __restrict__ J, int js,
                                                        const int* __restrict__ parents, const float* __restrict__ dA,
                                                        const float* __restrict__ dAt, const float* __restrict__ dJP,
+                                                       const float* __restrict__ dF, int ldf,
                                                        float* __restrict__ dR, float* __restrict__ dJ, int N) {
   __shared__ int sp[NJ];
   __shared__ __align__(16) float sG[CW][NJ * 12];
@@ -281,7 +282,8 @@ __global__ void __launch_bounds__(CW * 32) k_chain_bwd(const float* __restrict__
       }
     }
     __syncwarp();
-    for (int k = lane; k < 216; k += 32) dR[n * 216 + k] = sR[k];
+    // + the gradient of the pose feature (R[1:] - I), which reaches the rotations of joints 1..23 directly
+    for (int k = lane; k < 216; k += 32) dR[n * 216 + k] = sR[k] + ((dF != nullptr && k >= 9) ? __ldg(dF + n * ldf + (k - 9)) : 0.f);
     if (dJ != nullptr && lane < NJ) {
       if (js != 0) {
 #pragma unroll
@@ -330,12 +332,19 @@ extern "C" int nemo_b200_chain_fwd(const float* R, const float* J, int j_stride,
   return nemo_b200_pose_chain_fwd(R, nullptr, 0, 0, nullptr, J, j_stride, parents, nullptr, nullptr, 0, A, JP, N, stream);
 }
 
-extern "C" int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents, const float* dA,
-                                   const float* dAt, const float* dJP, float* dR, float* dJ, int N, void* stream) {
+extern "C" int nemo_b200_chain_bwd2(const float* R, const float* J, int j_stride, const int* parents, const float* dA,
+                                    const float* dAt, const float* dJP, const float* dF, int ldf, float* dR, float* dJ,
+                                    int N, void* stream) {
   if (N == 0) return 0;
   NB_REQUIRE(R && J && parents && dR && N >= 0 && (j_stride == 0 || j_stride == 72), "chain_bwd: bad args");
+  NB_REQUIRE(dF == nullptr || ldf >= 207, "chain_bwd: ldf >= 207");
   // shared joints accumulate with one atomic per value and CTA: fewer, longer CTAs
   const int grid = (dJ && j_stride == 0) ? min(cdiv(N, CW), num_sms()) : chain_grid(N);
-  k_chain_bwd<<<grid, CW * 32, 0, S(stream)>>>(R, J, j_stride, parents, dA, dAt, dJP, dR, dJ, N);
+  k_chain_bwd<<<grid, CW * 32, 0, S(stream)>>>(R, J, j_stride, parents, dA, dAt, dJP, dF, ldf, dR, dJ, N);
   NB_LAUNCH_CHECK("chain_bwd");
+}
+
+extern "C" int nemo_b200_chain_bwd(const float* R, const float* J, int j_stride, const int* parents, const float* dA,
+                                   const float* dAt, const float* dJP, float* dR, float* dJ, int N, void* stream) {
+  return nemo_b200_chain_bwd2(R, J, j_stride, parents, dA, dAt, dJP, nullptr, 0, dR, dJ, N, stream);
 }

@@ -343,15 +343,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             }
             sts128(a16, make_float4(x[0], x[1], x[2], x[3]));   // own chunk: read (gate) before write, same thread
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (p.splits > 1 || p.accumulate) tma_reduce_add_2d(&tmC, box, n0, m_base);
-            else tma_store_2d(&tmC, box, n0, m_base);
-            bulk_commit();
-            bulk_wait_read0();   // the box is reused by the next pass / tile
+          if (p.splits > 1 || p.accumulate) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmC, box, n0, m_base);
+              bulk_commit();
+              bulk_wait_read0();   // the box is reused by the next pass / tile
+            }
+            __syncwarp();
+          } else {
+            // plain store: the box is read back row-wise (eight lanes per 128-byte row, four rows per instruction) and
+            // written with 16-byte stores -- four full row segments per instruction; see gemm_tc2.cu
+            __syncwarp();
+            const int nn = n0 + 4 * (lane & 7);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + (lane >> 3);
+              const float4 v = lds128(box + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+              if (m_base + r < p.M && nn < p.N)
+                *reinterpret_cast<float4*>(p.C + (size_t)(m_base + r) * p.ldc + nn) = v;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         continue;
       }

@@ -56,7 +56,10 @@ struct Params {
   int M, N, K, act, accumulate, splits, mtiles, ntiles, kblocks, flush;
   float gslope;
   const float* bias;
+  float* C;
+  int ldc;
   int has_gate;
+  unsigned long long* dbg;   // NEMO_B200_GEMM_TIMING: clock stamps of CTA 0
 };
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -78,6 +81,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto stamp = [&](int i) {
+    if (p.dbg && blockIdx.x == 0) p.dbg[i] = (unsigned long long)clock64();
+  };
+  if (threadIdx.x == 0) stamp(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -97,6 +104,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32u(tmem_slot);
+  if (threadIdx.x == 0) stamp(1);
 
   const int units = p.mtiles * p.ntiles * p.splits;
   constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, B_MN ? 1 : 0);  // A is K-major in TMEM whatever its source
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int s = it % STAGES;
             mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+            if (it == 0) stamp(2);
             mbar_arrive_expect_tx(full(s), RAW_BYTES);
             const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
             if (!A_MN) {
@@ -152,6 +161,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
             for (int kb = kc; kb < kce; ++kb, ++it) {
               const int s = it % STAGES;
               mbar_wait(conv(s), (it / STAGES) & 1);
+              if (it == 0) stamp(4);
+              if (it == 16) stamp(10);
+              if (it == 48) stamp(11);
               tc_fence_after();
               const uint32_t a_hi = tmem_base + TMEM_A + s * (2 * BK), a_lo = a_hi + BK;
               const uint32_t b_hi = sbase + s * STAGE_BYTES + A_BYTES, b_lo = b_hi + B_BYTES;
@@ -173,6 +185,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
             umma_commit(pfull);
           }
         }
+        stamp(5);
       }
       __syncwarp();
     }
@@ -189,6 +202,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
         const int s = it % STAGES;
         const uint32_t sa = sbase + s * STAGE_BYTES;
         mbar_wait(full(s), (it / STAGES) & 1);
+        if (it == 0 && threadIdx.x == 128) stamp(3);
         uint32_t h[BK], w[BK];
         if (!A_MN) {
           // K-major raw tile: row r = 64 bytes, 16-byte chunk c stored at chunk c ^ ((r >> 1) & 3)
@@ -278,6 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
         }
         tc_fence_before();
         mbar_arrive(pempty);  // folded: the MMA warp may overwrite the accumulator
+        if (threadIdx.x == 256) stamp(6);
       }
       const int m_base = mb * BM + q * 32;
       const int ncol0 = nb * BN + hc * NC;
@@ -327,26 +342,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc2(const __grid_consta
             }
           }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const bool red = p.splits > 1 || p.accumulate;
-          if (red) tma_reduce_add_2d(&tmC, box0, n_rd, m_base);
-          else tma_store_2d(&tmC, box0, n_rd, m_base);
-          if (two) {
-            if (red) tma_reduce_add_2d(&tmC, box0 + BOX_BYTES, n_rd + 32, m_base);
-            else tma_store_2d(&tmC, box0 + BOX_BYTES, n_rd + 32, m_base);
+        const bool red = p.splits > 1 || p.accumulate;
+        if (red) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmC, box0, n_rd, m_base);
+            if (two) tma_reduce_add_2d(&tmC, box0 + BOX_BYTES, n_rd + 32, m_base);
+            bulk_commit();
+            bulk_wait_read0();   // the boxes are reused by the next round / tile
           }
-          bulk_commit();
-          bulk_wait_read0();   // the boxes are reused by the next round / tile
+          __syncwarp();
+        } else {
+          // plain store: read the boxes back row-wise -- eight lanes per 128-byte row, four rows per instruction -- and
+          // write them with 16-byte stores: every instruction covers four full 128-byte row segments.  (A TMA store
+          // drains ~16 bytes per cycle and SM: 8.8k cycles for a 128 x 256 tile, exposed when a CTA owns one tile and
+          // competing with the operand loads otherwise; measured, NEMO_B200_GEMM_TIMING.)
+          __syncwarp();
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int n0 = n_rd + 32 * b + 4 * (lane & 7);
+            if (n_rd + 32 * b < p.N) {  // warp-uniform
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3);
+                const float4 v = lds128(box0 + b * BOX_BYTES + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+                if (m_base + r < p.M && n0 < p.N)
+                  *reinterpret_cast<float4*>(p.C + (size_t)(m_base + r) * p.ldc + n0) = v;
+              }
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
+    if (threadIdx.x == 256) stamp(7);
     if (lane == 0) bulk_wait_all();
+    if (threadIdx.x == 256) stamp(8);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(9);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -408,6 +444,25 @@ template <bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tg, const Params& p,
            int grid, cudaStream_t s) {
   NB_SET_SMEM_ONCE((k_gemm_tc2<A_MN, B_MN>), SMEM_BYTES);
+  static const int timing = [] { const char* e = getenv("NEMO_B200_GEMM_TIMING"); return e ? atoi(e) : 0; }();
+  if (timing) {   // debug: one launch, synchronise, print CTA 0's timeline (cycles since kernel entry)
+    static unsigned long long* dbg = nullptr;
+    if (!dbg) NB_CUDA(cudaMalloc(&dbg, 16 * sizeof(unsigned long long)));
+    NB_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), s));
+    Params q = p;
+    q.dbg = dbg;
+    k_gemm_tc2<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, tc, tg, q);
+    NB_CUDA(cudaStreamSynchronize(s));
+    unsigned long long h[16];
+    NB_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    static const char* names[12] = {"entry", "setup done", "first TMA", "first full (A conv)", "first MMA", "last MMA issued",
+                                    "last partial folded", "epilogue issued", "stores performed", "all warps done",
+                                    "k-block 16 issued", "k-block 48 issued"};
+    fprintf(stderr, "[gemm_tc2 timing] M=%d N=%d K=%d grid=%d splits=%d flush=%d:", p.M, p.N, p.K, grid, p.splits, p.flush);
+    for (int i = 1; i < 12; ++i) fprintf(stderr, "  %s %lld", names[i], h[i] ? (long long)(h[i] - h[0]) : -1LL);
+    fprintf(stderr, "\n");
+    return 0;
+  }
   k_gemm_tc2<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, tc, tg, p);
   NB_LAUNCH_CHECK("gemm_tc2");
 }
@@ -440,6 +495,8 @@ int gemm_tc2(const float* A, const float* B, const float* bias, float* C, int M,
   Params p;
   p.M = M; p.N = N; p.K = K; p.act = act; p.accumulate = accumulate; p.gslope = gslope; p.bias = bias;
   p.has_gate = gate != nullptr;
+  p.dbg = nullptr;
+  p.C = C; p.ldc = ldc;
   p.mtiles = cdiv(M, BM);
   p.ntiles = cdiv(N, BN);
   p.kblocks = cdiv(K, BK);

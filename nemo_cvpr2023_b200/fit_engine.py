@@ -420,7 +420,7 @@ class FitEngine:
         w = dict(
             raw=z(N), X=z(Np, self.ldx), warped=z(N), yn=z(self.V, 3),
             H1=z(Np, h), H2=z(Np, h), H3=z(Np, h), Y=z(Np, LDY),
-            R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, LDF), F_m=z(N, LDF),
+            R=z(N, 24, 9), aa=z(N, 72), trans=z(N, 3), F=z(N, LDF), F_m=z(N, LDF), dF_m=z(N, LDF), dF_o=z(N, LDF),
             PO_m=z(N, 3 * VP), PO_o=z(N, 3 * VP), PO_r=z(N, 3 * VP), dPO=z(N, 3 * VP),
             A_m=z(N, 288), A_o=z(N, 288), A_r=z(N, 288), JP=z(N, 72), JPs=z(N, 72),
             R_o=z(N, 24, 9), R_r=z(N, 24, 9),
@@ -552,15 +552,18 @@ class FitEngine:
             if nq:
                 lib.readout_bwd(w['A_m'], w['Z'], ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], w['dJX'],
                                 w['dA'], 0, w['dZ'], N)
-            lib.chain_bwd(w['R'], w['J'], 0, C.parents, w['dA'] if nq else None, None, w['dJP'], dR,
-                          w['dJ_m'].zero_() if self.compute_betas_grad else None, N)
+            # the read-outs' gradient with respect to the pose feature first (its own aligned rows: tensor-core GEMM with
+            # the TMA epilogue), then the chain backward adds it into dR[:, 1:] while it writes dR.  V4 opt_cam
+            # (:4060-4149) detaches the body rotmats: the gradient reaches the MLP through the global orientation and
+            # the translation only.
+            dF = None
+            if nq and not detach_pose:
+                dF = w['dF_m']
+                gemm(w['dZ'], ro['MZ'], dF, N, 207, ro['ldz'], ro['ldz'], ro['ldz'], LDF, transB=True)
+            lib.chain_bwd2(w['R'], w['J'], 0, C.parents, w['dA'] if nq else None, None, w['dJP'], dF, LDF, dR,
+                           w['dJ_m'].zero_() if self.compute_betas_grad else None, N)
             if detach_pose:
-                # V4 opt_cam (:4060-4149): body rotmats detached, gradient reaches the MLP through the global
-                # orientation and the translation only
                 dR[:, 1:].zero_()
-            elif nq:
-                gemm(w['dZ'], ro['MZ'], dR.view(-1)[9:], N, 207, ro['ldz'], ro['ldz'], ro['ldz'], 216, transB=True,
-                     accumulate=True)
             if self.compute_betas_grad:
                 w['dJ'].copy_(w['dJ_m'])
                 self._betas_grad(w, N, first=True, mesh=False)
@@ -635,10 +638,9 @@ class FitEngine:
             if full and w_vp:
                 lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, None, w['signs'], ls * w_vp / (N * NV * 3.0),
                              w['dPO'], w['dAs'], N)
-                lib.chain_bwd(w['R_o'], w['J'], 0, C.parents, w['dAs'], None, None, w['dR_o'],
-                              w['dJ'].zero_() if self.compute_betas_grad else None, N)
-                gemm(w['dPO'], C.PD, w['dR_o'].view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True,
-                     accumulate=True)
+                gemm(w['dPO'], C.PD, w['dF_o'], N, 207, 3 * VP, 3 * VP, 3 * VP, LDF, transB=True)
+                lib.chain_bwd2(w['R_o'], w['J'], 0, C.parents, w['dAs'], None, None, w['dF_o'], LDF, w['dR_o'],
+                               w['dJ'].zero_() if self.compute_betas_grad else None, N)
                 if self.compute_betas_grad:
                     self._betas_grad(w, N, first=not need_2d, mesh=True)
                 lib.rodrigues_bwd(w['aa'].view(-1)[3:], 72, w['dR_o'].view(-1)[9:], 216, w['d_aa'].view(-1)[3:], 72,

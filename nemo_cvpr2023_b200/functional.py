@@ -444,12 +444,16 @@ class _LBS(torch.autograd.Function):
             dA = dAs if dA is None else dA.add_(dAs)
         dR = _new((N, 24, 9), rot)
         dJ = _new((N, 72), rot) if ctx.per_frame else torch.zeros(72, device=rot.device)
-        lib.chain_bwd(rot, J, ctx.js, C.parents, dA, None, dJP, dR, dJ, N)
-        # dR[:, 1:] += d(pose feature), written in place through the leading dimension (pose_feature backward)
-        if dPO is not None:
-            gemm(dPO, C.PD, dR.view(-1)[9:], N, 207, 3 * VP, 3 * VP, 3 * VP, 216, transB=True, accumulate=True)
-        if dZ is not None:
-            gemm(dZ, ro['MZ'], dR.view(-1)[9:], N, 207, ldz, ldz, ldz, 216, transB=True, accumulate=True)
+        # d(pose feature) into its own aligned rows (tensor-core GEMMs with the TMA epilogue), added into dR[:, 1:] by the
+        # chain backward as it writes dR
+        dF = None
+        if dPO is not None or dZ is not None:
+            dF = _new((N, 208), rot)
+            if dPO is not None:
+                gemm(dPO, C.PD, dF, N, 207, 3 * VP, 3 * VP, 3 * VP, 208, transB=True)
+            if dZ is not None:
+                gemm(dZ, ro['MZ'], dF, N, 207, ldz, ldz, ldz, 208, transB=True, accumulate=dPO is not None)
+        lib.chain_bwd2(rot, J, ctx.js, C.parents, dA, None, dJP, dF, 208, dR, dJ, N)
         dbetas = None
         if ctx.needs_input_grad[1]:
             MZs = ro['MZ'][207:]

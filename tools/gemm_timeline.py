@@ -13,6 +13,6 @@ for (M, N, K, ta, tb) in [(4096, 512, 72, 0, 1), (4096, 512, 512, 0, 1), (4097, 
     A = torch.randn((K, r4(M)) if ta else (M, r4(K)), device='cuda')
     B = torch.randn((N, r4(K)) if tb else (K, r4(N)), device='cuda')
     C = torch.empty(M, r4(N), device='cuda')
-    for _ in range(3):
-        lib.gemm_tc(A, B, None, C, M, N, K, A.shape[1], B.shape[1], r4(N), ta, tb, 0, None, 0, 0.0, 0, 0)
+    for _ in range(2):
+        lib.gemm(A, B, None, C, M, N, K, A.shape[1], B.shape[1], r4(N), ta, tb, 0, None, 0, 0.0, 0)
     torch.cuda.synchronize()
