@@ -271,6 +271,12 @@ int nemo_b200_monotonic_bwd(const float* x, const float* shifts, const float* sc
 int nemo_b200_gmm_prior(const float* pose, int ldp, const float* means, const float* precisions,
                         const float* nll_weights, int M, int D, float* ll,
                         float gscale, float* dpose, int ldd, int accumulate, int N, void* stream);
+/* The precisions are frozen buffers: nemo_b200_gmm_prepare symmetrises them once into prec_sym (M, 69, 72) (rows padded
+ * to 16 bytes, 0.5 (P + P^T)) and nemo_b200_gmm_prior_sym is nemo_b200_gmm_prior reading that table. */
+int nemo_b200_gmm_prepare(const float* precisions, int M, int D, float* prec_sym, void* stream);
+int nemo_b200_gmm_prior_sym(const float* pose, int ldp, const float* means, const float* prec_sym,
+                            const float* nll_weights, int M, int D, float* ll,
+                            float gscale, float* dpose, int ldd, int accumulate, int N, void* stream);
 /* VPoser posterior head (vposer_model.py:48-56) + KL(N(mu,sigma)||N(0,1)) of vposer_loss (:2798-2803).
  * head (N,2L) = [mu | pre-softplus]; kl_acc[0] += sum_n sum_d KL; sigma (N,L) out (may be NULL);
  * dhead (N,2L) = gscale * d(sum KL)/d head (may be NULL). */

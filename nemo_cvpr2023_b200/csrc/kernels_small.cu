@@ -498,7 +498,8 @@ __global__ void k_embed_fwd(const float* __restrict__ raw, const int64_t* __rest
   for (int c = lane; c < C; c += 32)
     x[nf + c] = (n < N) ? codes[(size_t)v * C + c] + (noise ? noise[(size_t)n * C + c] : 0.f) : 0.f;
 }
-// block = 8 warps, each warp strides over the block's samples; dlog_sigmas reduced in the block first
+// block = 8 warps, each warp takes a run of the block's samples; dlog_sigmas reduced in the block first
+constexpr int EB_KPL = 8;   // phase-network nodes per lane held in registers: K <= 256
 __global__ void __launch_bounds__(256) k_embed_bwd(const float* __restrict__ raw, const int64_t* __restrict__ vi,
                                                    const float* __restrict__ shifts, const float* __restrict__ scales,
                                                    int K, const float* __restrict__ centres,
@@ -514,7 +515,31 @@ __global__ void __launch_bounds__(256) k_embed_bwd(const float* __restrict__ raw
   float* myls = sm + (size_t)w * (D > 0 ? D : 1);
   for (int i = lane; i < D; i += 32) myls[i] = 0.f;
   int n0 = blockIdx.x * per_block;
-  for (int s = w; s < per_block; s += 8) {
+  float asc[EB_KPL], ash[EB_KPL], g0acc = 0.f, g1acc = 0.f, cacc = 0.f;
+#pragma unroll
+  for (int t = 0; t < EB_KPL; ++t) asc[t] = ash[t] = 0.f;
+  int cur_v = -1;
+  auto flush = [&]() {
+    if (cur_v < 0) return;
+#pragma unroll
+    for (int t = 0; t < EB_KPL; ++t) {
+      const int k = lane + 32 * t;
+      if (k < K) {
+        if (asc[t] != 0.f) atomicAdd(dsc + (size_t)cur_v * K + k, asc[t]);
+        if (ash[t] != 0.f) atomicAdd(dsh + (size_t)cur_v * K + k, ash[t]);
+      }
+      asc[t] = ash[t] = 0.f;
+    }
+    if (lane == 0) {   // every lane carries the same sums
+      atomicAdd(gy01 + 2 * cur_v, g0acc);
+      atomicAdd(gy01 + 2 * cur_v + 1, g1acc);
+    }
+    if (dcodes && lane < C && cacc != 0.f) atomicAdd(dcodes + (size_t)cur_v * C + lane, cacc);
+    g0acc = g1acc = cacc = 0.f;
+  };
+  // a warp takes a contiguous run of the block's samples
+  const int per_warp = per_block / 8;
+  for (int s = w * per_warp; s < (w + 1) * per_warp; ++s) {
     int n = n0 + s;
     if (n > N) break;
     const float* dx = dX + (size_t)n * ldx;
@@ -534,26 +559,36 @@ __global__ void __launch_bounds__(256) k_embed_bwd(const float* __restrict__ raw
     } else gph = dx[0];
     if (n >= N) continue;
     int v = (int)vi[n];
-    if (dcodes)
-      for (int c = lane; c < C; c += 32) atomicAdd(dcodes + (size_t)v * C + c, dx[nf + c]);
-    // monotonic network backward
+    const float dcode_n = (dcodes && lane < C) ? dx[nf + lane] : 0.f;   // instance codes: C <= 32 (checked by the host)
+    // monotonic network backward.  The per-node gradients of the sample's view accumulate in registers while the warp's
+    // consecutive samples share a view (batches are usually sorted by view or cover whole views) and go out as one
+    // atomic per node when the view changes: 4096 samples x 200 nodes x 2 atomics on 3200 addresses were the cost of
+    // this kernel.
     float den = yn[3 * v + 2];
     float gy = gph / den;
-    if (lane == 0) {
-      atomicAdd(gy01 + 2 * v, gph * (ph - 1.f) / den);
-      atomicAdd(gy01 + 2 * v + 1, -gph * ph / den);
+    if (v != cur_v) {
+      flush();
+      cur_v = v;
     }
+    g0acc += gph * (ph - 1.f) / den;
+    g1acc += -gph * ph / den;
+    cacc += dcode_n;
     const float* sh = shifts + (size_t)v * K;
     const float* sc = scales + (size_t)v * K;
     float u = raw[n];
-    for (int k = lane; k < K; k += 32) {
-      float a = fmaxf(sc[k], 0.f), b = fmaxf(sh[k], 0.f);
-      float sg = sigmoidf_(a * (u - b));
-      float dz = gy * sg * (1.f - sg) / (float)K;
-      if (sc[k] > 0.f) atomicAdd(dsc + (size_t)v * K + k, dz * (u - b));
-      if (sh[k] > 0.f) atomicAdd(dsh + (size_t)v * K + k, -dz * a);
+#pragma unroll
+    for (int t = 0; t < EB_KPL; ++t) {
+      const int k = lane + 32 * t;
+      if (k < K) {
+        float a = fmaxf(sc[k], 0.f), b = fmaxf(sh[k], 0.f);
+        float sg = sigmoidf_(a * (u - b));
+        float dz = gy * sg * (1.f - sg) / (float)K;
+        if (sc[k] > 0.f) asc[t] += dz * (u - b);
+        if (sh[k] > 0.f) ash[t] += -dz * a;
+      }
     }
   }
+  flush();
   __syncthreads();
   if (D > 0 && dls)
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
@@ -596,8 +631,9 @@ extern "C" int nemo_b200_embed_bwd(const float* raw_phase, const int64_t* view_i
                                    float* dlog_sigmas, float* dshifts, float* dscales, float* dcodes, float* scratch,
                                    int N, int V, void* stream) {
   NB_REQUIRE(raw_phase && view_idx && shifts && scales && warped && yn && dX && dshifts && dscales && scratch &&
-                 K > 0 && N >= 0 && V > 0 && D >= 0 && (D == 0 || (centres && log_sigmas && dlog_sigmas)),
-             "embed_bwd: bad args");
+                 K > 0 && K <= 32 * EB_KPL && C <= 32 && N >= 0 && V > 0 && D >= 0 &&
+                 (D == 0 || (centres && log_sigmas && dlog_sigmas)),
+             "embed_bwd: bad args (at most 256 phase-network nodes, 32 instance-code entries)");
   NB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * V, S(stream)));
   const int per_block = 64;
   size_t smem = sizeof(float) * 8 * (D > 0 ? D : 1);
@@ -707,7 +743,7 @@ constexpr int GD = 69, GDP = 72;
 __global__ void __launch_bounds__(256) k_gmm(const float* __restrict__ pose, int ldp, const float* __restrict__ means,
                                              const float* __restrict__ prec, const float* __restrict__ nllw, int M,
                                              float* __restrict__ ll, float gscale, float* __restrict__ dpose, int ldd,
-                                             int acc, int N) {
+                                             int acc, int N, const float* __restrict__ psym) {
   __shared__ __align__(16) float sP[GD * GDP];     // symmetrised precision of the current component, rows padded to 72
   __shared__ float sD[GDP][33];      // d[j][sample]
   __shared__ float sQ[8][32];
@@ -724,9 +760,15 @@ __global__ void __launch_bounds__(256) k_gmm(const float* __restrict__ pose, int
   for (int r = 0; r < 9; ++r) ybest[r] = 0.f;
   for (int m = 0; m < M; ++m) {
     __syncthreads();
-    for (int i = threadIdx.x; i < GD * GD; i += 256) {
-      int a = i / GD, b = i % GD;
-      sP[a * GDP + b] = 0.5f * (prec[((size_t)m * GD + a) * GD + b] + prec[((size_t)m * GD + b) * GD + a]);
+    if (psym) {   // symmetrised rows padded to 72 floats, prepared once (nemo_b200_gmm_prepare): straight 16-byte copies
+      const float4* src = reinterpret_cast<const float4*>(psym + (size_t)m * GD * GDP);
+      float4* dst = reinterpret_cast<float4*>(sP);
+      for (int i = threadIdx.x; i < GD * GDP / 4; i += 256) dst[i] = __ldg(src + i);
+    } else {
+      for (int i = threadIdx.x; i < GD * GD; i += 256) {
+        int a = i / GD, b = i % GD;
+        sP[a * GDP + b] = 0.5f * (prec[((size_t)m * GD + a) * GD + b] + prec[((size_t)m * GD + b) * GD + a]);
+      }
     }
     float d[GDP];
 #pragma unroll
@@ -744,13 +786,19 @@ __global__ void __launch_bounds__(256) k_gmm(const float* __restrict__ pose, int
       int i = w * 9 + r;
       float a = 0.f;
       if (i < GD) {
-        // the row is a warp-wide broadcast: 16-byte loads quarter the LSU instructions that pace this kernel
+        // the row is a warp-wide broadcast (16-byte loads); four independent partial sums: one 72-long dependent FMA
+        // chain per row was the critical path of this kernel
         const float4* row = reinterpret_cast<const float4*>(sP + i * GDP);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
         for (int j = 0; j < GDP / 4; ++j) {
           const float4 p4 = row[j];
-          a += p4.x * d[4 * j] + p4.y * d[4 * j + 1] + p4.z * d[4 * j + 2] + p4.w * d[4 * j + 3];
+          a0 = fmaf(p4.x, d[4 * j], a0);
+          a1 = fmaf(p4.y, d[4 * j + 1], a1);
+          a2 = fmaf(p4.z, d[4 * j + 2], a2);
+          a3 = fmaf(p4.w, d[4 * j + 3], a3);
         }
+        a = (a0 + a1) + (a2 + a3);
         q += a * sD[i][lane];
       }
       y[r] = a;
@@ -788,8 +836,30 @@ extern "C" int nemo_b200_gmm_prior(const float* pose, int ldp, const float* mean
   NB_REQUIRE(pose && means && precisions && nll_weights && M > 0 && D == GD && ldp >= D && N >= 0,
              "gmm_prior: bad args (D must be 69)");
   k_gmm<<<cdiv(N, 32), 256, 0, S(stream)>>>(pose, ldp, means, precisions, nll_weights, M, ll, gscale, dpose, ldd,
-                                            accumulate, N);
+                                            accumulate, N, nullptr);
   NB_LAUNCH_CHECK("gmm_prior");
+}
+// The precision matrices are frozen buffers (hmr/smplify/prior.py:142-160): symmetrise and pad them once.
+__global__ void k_gmm_prepare(const float* __restrict__ prec, float* __restrict__ psym, int M) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * GD * GDP) return;
+  int m = i / (GD * GDP), a = (i / GDP) % GD, b = i % GDP;
+  psym[i] = b < GD ? 0.5f * (prec[((size_t)m * GD + a) * GD + b] + prec[((size_t)m * GD + b) * GD + a]) : 0.f;
+}
+extern "C" int nemo_b200_gmm_prepare(const float* precisions, int M, int D, float* prec_sym, void* stream) {
+  NB_REQUIRE(precisions && prec_sym && M > 0 && D == GD, "gmm_prepare: bad args (D must be 69)");
+  k_gmm_prepare<<<NB_1D((long long)M * GD * GDP)>>>(precisions, prec_sym, M);
+  NB_LAUNCH_CHECK("gmm_prepare");
+}
+extern "C" int nemo_b200_gmm_prior_sym(const float* pose, int ldp, const float* means, const float* prec_sym,
+                                       const float* nll_weights, int M, int D, float* ll, float gscale, float* dpose,
+                                       int ldd, int accumulate, int N, void* stream) {
+  if (N == 0) return 0;
+  NB_REQUIRE(pose && means && prec_sym && nll_weights && M > 0 && D == GD && ldp >= D && N >= 0 &&
+                 ((uintptr_t)prec_sym & 15) == 0, "gmm_prior_sym: bad args (D must be 69, prec_sym 16-byte aligned)");
+  k_gmm<<<cdiv(N, 32), 256, 0, S(stream)>>>(pose, ldp, means, nullptr, nll_weights, M, ll, gscale, dpose, ldd, accumulate,
+                                            N, prec_sym);
+  NB_LAUNCH_CHECK("gmm_prior_sym");
 }
 
 // =============================================================================== VPoser KL head

@@ -279,6 +279,8 @@ class FitEngine:
         self.vp = fold_vposer(vposer_sd, self.dev)
         f32 = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.dev).contiguous()
         self.gmm_means, self.gmm_prec, self.gmm_w = f32(gmm['means']), f32(gmm['precisions']), f32(gmm['nll_weights']).reshape(-1)
+        self.gmm_psym = torch.empty(self.gmm_means.shape[0], 69, 72, device=self.dev)   # symmetrised once: frozen buffer
+        lib.gmm_prepare(self.gmm_prec, self.gmm_means.shape[0], 69, self.gmm_psym)
         self.gt2d = f32(data['points2d_gt_all'])
         self.bbox = f32(data['gt_bbox_size'])
         self.hmr_theta = f32(data['hmr_theta']) if 'hmr_theta' in data else None
@@ -612,8 +614,9 @@ class FitEngine:
             self._lbs_forward(w, N, w['R_r'], w['PO_r'], w['A_r'], w['JPs'], aa=w['recon'], lda=69)
             lib.skin_l1_fwd(w['A_o'], w['PO_o'], w['A_r'], w['PO_r'], w['base'], C.Wt, w['signs'], acc[0:1], N)
             # GMM prior (:2758-2773): value and (scaled) gradient in one pass
-            lib.gmm_prior(w['aa'].view(-1)[3:], 72, self.gmm_means, self.gmm_prec, self.gmm_w, self.gmm_means.shape[0],
-                          69, w['ll'], ls * w_gmm / N, w['d_aa'].view(-1)[3:] if update else None, 72, 1, N)
+            lib.gmm_prior_sym(w['aa'].view(-1)[3:], 72, self.gmm_means, self.gmm_psym, self.gmm_w,
+                              self.gmm_means.shape[0], 69, w['ll'], ls * w_gmm / N,
+                              w['d_aa'].view(-1)[3:] if update else None, 72, 1, N)
             lib.colsum(w['ll'], acc[3:4], N, 1, 1, 1)
         if w_3d or (self.version >= 3 and full and getattr(a, 'weight_3d_loss', 0.0)):
             lib.pose3d_loss(w['aa'].view(-1)[3:], 72, vi, fi, self.hmr_theta, self.hmr_mask, 100.0, ls * w_3d, acc[2:3],
