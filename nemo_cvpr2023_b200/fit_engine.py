@@ -188,6 +188,7 @@ def fold_vposer(sd, device):
 
 
 _NVTX = bool(int(__import__('os').environ.get('NEMO_B200_NVTX', '0')))
+_DP_DRY = bool(int(__import__('os').environ.get('NEMO_B200_DP_DRY', '0')))
 
 
 class _Range:
@@ -360,6 +361,8 @@ class FitEngine:
 
     def _dp_finish(self, plain=False):
         import torch.distributed as dist
+        if _DP_DRY:      # debug (NEMO_B200_DP_DRY=1): everything but the collective, to separate its cost from the rest
+            return
         if self.dp_overlap and not plain:
             self._dp_bucket('tail')
         else:

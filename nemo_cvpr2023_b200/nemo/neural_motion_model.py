@@ -713,7 +713,11 @@ class NemoV4(NemoV3):
 
 
 class NemoV0(MultiViewModel):
-    """:3127-3361 (separate RotNet / FCNN per quantity).  Not run by any shipped script; not built."""
+    """:3127-3361 (separate RotNet / RotNet / FCNN for pose, orientation and translation).  Dead code in the reference:
+    the class defines no `get_preds_batch` (its `step` :3277 and `warmup` :3243 call it), `step` adds
+    `weight_vp_loss * vposer_loss(...)` where `vposer_loss` returns a tuple (:3337, a TypeError), `warmup` reads a
+    `spin_theta` track no loader provides, and no shipped script or config selects it.  There is no behaviour to
+    reproduce, so it is not part of the accelerated path; `RotNet` / `FCNN` themselves are available above."""
 
     def __init__(self, *a, **k):
-        raise NotImplementedError('NemoV0 is outside the accelerated path; use NemoV1..V4')
+        raise NotImplementedError('NemoV0 cannot run in the reference either (see the class docstring); use NemoV1..V4')
