@@ -865,9 +865,15 @@ int skin_l1_fwd2(const float* A_a, const float* PO_a, const float* A_b, const fl
                  const float* Wt, uint32_t* signs, float* l1_sum, int N, cudaStream_t s);
 void skin_chunking(int N, int frames_per_group, int ctas_per_sm, double setup, int max_chunks, int& groups_per_chunk,
                    int& nchunks);
+int skin_bwd2(const float* A, const float* PO, const float* base, const float* Wt, const float* dV,
+              const uint32_t* signs, float sign_scale, float* dPO, float* dA, int N, cudaStream_t s);
 }  // namespace nb
 
 namespace {
+static int bwd_generation() {
+  static const int g = [] { const char* e = getenv("NEMO_B200_SKIN_BWD"); return e ? atoi(e) : 2; }();
+  return g;
+}
 static int fwd_generation() {
   static const int g = [] { const char* e = getenv("NEMO_B200_SKIN_FWD"); return e ? atoi(e) : 2; }();
   return g;
@@ -982,6 +988,9 @@ extern "C" int nemo_b200_skin_bwd(const float* A, const float* PO, const float* 
   if (N == 0) return 0;
   NB_REQUIRE(A && PO && base && Wt && dPO && dA && (dV || signs) && N >= 0, "skin_bwd: bad args");
   cudaStream_t s = S(stream);
+  // second generation: TMA tensor loads (PO and dV 16-byte aligned, which every cudaMalloc'ed / torch buffer is)
+  if (bwd_generation() >= 2 && ((uintptr_t)PO & 15) == 0 && ((uintptr_t)dV & 15) == 0)
+    return nb::skin_bwd2(A, PO, base, Wt, dV, signs, sign_scale, dPO, dA, N, s);
   SkinBwdArgs a{};
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.dV = dV; a.signs = signs;
   a.sign_scale = sign_scale; a.dPO = dPO; a.dA = dA; a.N = N;

@@ -53,6 +53,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, t0 = 0, armed = 0;
   while (true) {
+#ifdef NB_MBAR_SUSPEND_NS
+    // with a suspend-time hint the hardware parks the warp until the phase completes (or the hint expires): a waiting
+    // warp costs no issue slots, where a bare try_wait returns after a short system-defined time and has to be re-issued
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"((uint32_t)(NB_MBAR_SUSPEND_NS))
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -60,6 +71,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     if (done) break;
 #ifdef NB_MBAR_SLEEP
     __nanosleep(NB_MBAR_SLEEP);

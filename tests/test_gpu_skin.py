@@ -67,6 +67,41 @@ def test_skin_forward_and_backward_ragged(ctx, N):
     assert_grad(dAs.double().cpu().numpy(), dA_ref, TOL_GRAD_REL, 'dA N=%d' % N)
 
 
+@pytest.mark.parametrize('N', [19, 64])
+def test_skin_backward_wide_dynamic_range(ctx, N):
+    """The adjoint GEMM runs on scaled fp16 operand pairs: upstream gradients whose magnitude differs by many orders
+    between frames (and between the vertices of one frame), and all-zero frames, must come out at fp32 accuracy."""
+    Fn, lib, C, sm = ctx
+    A, PO = _inputs(N, 40 + N)
+    A32, PO32 = g32(A), g32(PO.reshape(N, -1))
+    A, PO = A32.double().cpu().numpy(), PO32.double().cpu().numpy().reshape(N, 3, 6912)
+    r = np.random.RandomState(7 + N)
+    dV = r.standard_normal((N, 6890, 3))
+    dV *= 10.0 ** r.uniform(-12, 6, size=(N, 1, 1))                    # per-frame magnitude
+    dV *= 10.0 ** (4 * (r.uniform(size=(N, 6890, 1)) > 0.999))        # a few vertices 1e4 x larger
+    dV[3] = 0.0
+    dV[5, :, 1:] = 0.0
+    dV32 = g32(dV)
+    dV = dV32.double().cpu().numpy()
+    dPO = torch.full((N, 3 * 6912), float('nan'), device=DEV)
+    dAs = torch.full((N, 24, 12), float('nan'), device=DEV)
+    lib.skin_bwd(A32, PO32, C.vt, C.Wt, dV32, None, 0.0, dPO, dAs, N)
+    _, p, T = _ref_skin(A, PO, sm)
+    ph = np.concatenate([p, np.ones_like(p[..., :1])], -1)
+    W = np.asarray(sm['lbs_weights'], np.float64)
+    dA_ref = np.einsum('vj,nvr,nvc->njrc', W, dV, ph).reshape(N, 24, 12)
+    got = dAs.double().cpu().numpy()
+    assert np.all(got[3] == 0)
+    for n in range(N):                                                  # per frame: the frames differ by 1e18
+        if np.abs(dA_ref[n]).max() > 0:
+            assert_grad(got[n], dA_ref[n], TOL_GRAD_REL, 'dA frame %d' % n)
+    dPO_ref = np.einsum('nvrc,nvr->ncv', T[..., :3], dV)
+    gp = dPO.double().cpu().numpy().reshape(N, 3, 6912)[:, :, :6890]
+    for n in range(N):
+        if np.abs(dPO_ref[n]).max() > 0:
+            assert_grad(gp[n], dPO_ref[n], TOL_GRAD_REL, 'dPO frame %d' % n)
+
+
 @pytest.mark.parametrize('N', [1, 5, 36, 131])
 def test_fused_l1_and_sign_backward(ctx, N):
     Fn, lib, C, sm = ctx

@@ -64,6 +64,9 @@ cases = [
     ('read-outs bwd: dA, dZ', 0,
      lambda: lib.readout_bwd(A, Z, ro['ldz'], ro['Wp'], ro['np'], ro['Sj'], ro['nx'], dJX, dA, 0, dZ, N)),
 ]
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ''
 for name, streams, fn in cases:
+    if ONLY and ONLY not in name:
+        continue
     t = timeit(fn)
     print('%-48s %.3f ms   %7.1f GB/s algorithmic (%d streams/frame)' % (name, t, streams * STREAM * N / t / 1e6, streams))
