@@ -43,11 +43,14 @@ constexpr int TILE_V = 128;
 constexpr int NT_V = VP / TILE_V;       // 54 vertex tiles
 constexpr int FB = 8;                   // frames per group
 constexpr int NROW = FB * 12;           // 96 columns of T / of each half of the adjoint accumulator
-constexpr int AM_BYTES = NROW * 128;    // one tf32 part of the group's transforms: K-major, row = (f,r,c), k = joint
+// The group's transforms as the MN-major tf32 B operand of the T GEMM: k row = joint (128 bytes = 32 of the (f,r,c)
+// columns, 32-byte chunk c stored at c ^ (k & 3)), three 32-wide n blocks -- the memory order of A (N,24,12), so a
+// writer thread moves float4s: raw fp32 as the hi part (the tensor core ignores the low 13 mantissa bits), x - trunc(x)
+// as the lo part.
+constexpr int AM_BLK = NJ * 128;        // one n block: 24 k rows
+constexpr int AM_PART = 3 * AM_BLK;     // hi (or lo) part: 9 216 bytes
 
-__host__ __device__ __forceinline__ constexpr uint32_t kmajor_sw128(int row, int k) {
-  return (uint32_t)(row * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2));
-}
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -94,48 +97,22 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// power-of-two scale of a frame pair from the maximum |G| of the tile: E = its biased exponent, clamped so that both
-// the scale 2^(140 - E) (largest element -> [2^13, 2^14)) and the drain's factor 2^(E - 148) (undoes it and the 2^8 of
-// W) are normal numbers
-constexpr int W_SCALE_LOG2 = 8;
+// power-of-two scale of a frame from the maximum |G| of the tile: E = its biased exponent, clamped so that both the
+// scale 2^(140 - E) (largest element -> [2^13, 2^14)) and the drain's factor 2^(E - 148) (undoes it and the 2^8 of W)
+// are normal numbers
+constexpr int W_SCALE_LOG2 = 8;  // W is handed to the tensor core as fp16 pairs of 2^8 W
 __device__ __forceinline__ int scale_exponent(const float4& m) {
   const float mm = fmaxf(fmaxf(m.x, m.y), fmaxf(m.z, m.w));
   const int E = (int)((__float_as_uint(mm) >> 23) & 0xffu);
   return min(max(E, 22), 254);
 }
 
-// The 96 producer threads turn the 3x4 transforms of the group's 8 frames into the K-major B operand of the T GEMM
-// (row = f*12 + (r,c), k = joint), tf32 hi / lo.  Thread pt owns elements pt, pt+96, pt+192 of every frame's 288.
-struct AmatWriter {
-  uint32_t off[3][2];
-  __device__ __forceinline__ void init(int pt) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int jc = pt + 96 * i, j = jc / 12, c = jc % 12;
-      off[i][0] = kmajor_sw128(c, j);
-      off[i][1] = kmajor_sw128(12 + c, j) - 12 * 128;
-    }
-  }
-  __device__ __forceinline__ void store(uint32_t am, const float (&x)[FB][3]) const {
-#pragma unroll
-    for (int s = 0; s < FB; ++s)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        float hi, lo;
-        tf32_split(x[s][i], hi, lo);
-        const uint32_t o = am + s * (12 * 128) + off[i][s & 1];
-        sts32(o, hi);
-        sts32(o + AM_BYTES, lo);
-      }
-  }
-};
-
 struct Cfg {
   // G: MN-major fp16 B operand, n = [hi (f,r,c) 0..95 | lo 96..191] in three 64-wide blocks, k = vertex:
   // [n block][k group of 8: 1024 B][k row: 128 B = 64 n][16-byte chunk j stored at j ^ (k & 7)]
   static constexpr int GB_BYTES = TILE_V * 128;
-  static constexpr int OFF_AM = 0;                       // 2 buffers x [hi][lo] x 12 KB
-  static constexpr int OFF_G = OFF_AM + 4 * AM_BYTES;
+  static constexpr int OFF_AM = 0;                       // 2 buffers x [hi][lo] x 9 KB
+  static constexpr int OFF_G = OFF_AM + 4 * AM_PART;
   // input ring: THREE TMA tensor copies per stage (a bulk-copy instruction costs its issuing warp ~125 cycles per
   // copy -- the 32 row copies per group of the first generation made the loader warp the slowest role of the kernel):
   //   pose offsets: 2-D tensor (N*3 rows x VP floats), box 128 x 24 = [frame][component][128 vertices]
@@ -161,14 +138,14 @@ struct Cfg {
   static constexpr int OFF_INV = OFF_SC + 512;            // the drain's factor per frame: [group & 3][frame]
   static constexpr int OFF_BARS = OFF_INV + 128;
   static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
-  static constexpr int TM_T = 0;        // T: 96 columns
-  static constexpr int TM_WT = 96;      // [W_hi^T ; W_lo^T] fp16: 64 columns (k = vertex, two per column)
-  static constexpr int TM_D = 160;      // dA: 192 columns [. G_hi | . G_lo], TWO M = 64 accumulators (lane offsets 0 / 16)
-  static constexpr int TM_W = 352;      // W tile, tf32: 32 hi + 32 lo columns
+  static constexpr int TM_T = 0;        // T: 2 x 96 columns (double buffered: the blend of the next group runs ahead)
+  static constexpr int TM_WT = 192;     // [W_hi^T ; W_lo^T] fp16: 64 columns (k = vertex, two per column)
+  static constexpr int TM_D = 256;      // dA: 192 columns [. G_hi | . G_lo], TWO M = 64 accumulators (lane offsets 0 / 16)
+  static constexpr int TM_W = 448;      // W tile, tf32: 32 hi + 32 lo columns
   static constexpr int TMEM_COLS = 512;
 };
 static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(Cfg::OFF_G % 1024 == 0 && Cfg::OFF_ST % 128 == 0 && Cfg::ST_BYTES % 128 == 0 &&
+static_assert(AM_BLK % 1024 == 0 && Cfg::OFF_G % 1024 == 0 && Cfg::OFF_ST % 128 == 0 && Cfg::ST_BYTES % 128 == 0 &&
               Cfg::ST_PO_BYTES % 128 == 0 && Cfg::OFF_STG % 16 == 0, "operand / TMA alignment");
 
 struct Args {
@@ -185,8 +162,10 @@ struct Args {
 };
 
 constexpr int TRACE_CTA = 60, TRACE_NG = 24;
-constexpr int W_PROD_ = 16, W_ISSUE_ = 19, W_DRAIN_ = 20, W_LOAD_ = 24, W_TISSUE_ = 25;
-constexpr int NWORK = 16;                 // worker warps: warp = 4 * (frame pair of the group) + (TMEM lane quarter)
+constexpr int FH_ = 2;  // = FH below
+constexpr int W_PROD_ = 4 * 8 / FH_, W_ISSUE_ = W_PROD_ + 3, W_DRAIN_ = W_PROD_ + 4, W_LOAD_ = W_PROD_ + 8, W_TISSUE_ = W_PROD_ + 9;
+constexpr int FH = FH_;                   // frames of the group per worker warp
+constexpr int NWORK = 4 * FB / FH;        // worker warps: warp = 4 * (frame subset of the group) + (TMEM lane quarter)
 constexpr int THREADS = (NWORK + 10) * 32;
 
 template <bool HAS_DV, bool HAS_SIGNS, bool TIMING>
@@ -212,7 +191,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = sbase + C_::OFF_BARS;
-  const uint32_t tfull = bars, tempty = bars + 8;               // T complete (commit) / read by the workers (512)
+  auto tfull = [&](int b) { return bars + 8u * b; };            // T[b] complete                     (commit)
+  auto tempty = [&](int b) { return bars + 8u * (28 + b); };    // T[b] read by the workers          (all worker threads)
   auto amfree = [&](int b) { return bars + 8u * (2 + b); };     // T GEMM done reading Amat[b]       (commit)
   auto amfull = [&](int b) { return bars + 8u * (26 + b); };    // Amat[b] written                   (96)
   auto d2full = [&](int b) { return bars + 8u * (4 + b); };     // dA[b] complete                    (commit)
@@ -238,9 +218,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
   const int last = a.N - 1;
 
   if (tid == 0) {
-    mbar_init(tfull, 1);
-    mbar_init(tempty, NWORK * 32);
     for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull(b), 1);
+      mbar_init(tempty(b), NWORK * 32);
       mbar_init(amfree(b), 1);
       mbar_init(amfull(b), 96);
       mbar_init(d2full(b), 1);
@@ -261,9 +241,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
   constexpr int W_PROD = NWORK, W_ISSUE = NWORK + 3, W_DRAIN = NWORK + 4, W_LOAD = NWORK + 8, W_TISSUE = NWORK + 9;
   static_assert(W_DRAIN % 4 == 0, "drain warp W_DRAIN + q reads TMEM lane quarter q");
   if (warp == W_ISSUE) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
-  // zero Amat: its pad columns k = 24..31 stay zero for the whole kernel (G is fully rewritten every group)
-  for (int i = tid; i < 4 * AM_BYTES / 16; i += THREADS)
-    sts128(sbase + C_::OFF_AM + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -315,23 +292,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  constexpr uint32_t idesc = umma_idesc_tf32(128, NROW, 0, 0);
+  constexpr uint32_t idesc = umma_idesc_tf32(128, NROW, 0, 1);      // B = Amat, MN-major
   constexpr uint32_t idesc_d = umma_idesc_f16(64, 2 * NROW, 0, 1);  // B = G, MN-major
 
   if (warp >= W_PROD && warp < W_ISSUE) {
     // ------------------------------------------------------------------ Amat writers (double buffered)
+    // float4 unit u = pt + 96 i of the group's 8 x 72: frame u / 72, joint (u % 72) / 3, quarter u % 3
     const int pt = tid - W_PROD * 32;
-    AmatWriter aw;
-    aw.init(pt);
-    float x[FB][3];
+    uint32_t dst[6];
+    int srcoff[6], fr[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int u = pt + 96 * i, f = u / 72, j = (u % 72) / 3, q = u % 3;
+      const int n = f * 12 + 4 * q, nb = n >> 5, np = n & 31;
+      dst[i] = sbase + C_::OFF_AM + nb * AM_BLK + j * 128 + ((((np >> 3) ^ j) & 3) << 5) + ((np >> 2) & 1) * 16;
+      srcoff[i] = j * 12 + 4 * q;
+      fr[i] = f;
+    }
+    float4 x[6];
     auto fetch = [&](int gi) {
       const int n0 = group_of(gi) * FB;
 #pragma unroll
-      for (int s = 0; s < FB; ++s) {
-        const float* p = a.A + (size_t)min(n0 + s, last) * 288 + pt;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) x[s][i] = __ldg(p + 96 * i);
-      }
+      for (int i = 0; i < 6; ++i)
+        x[i] = __ldg(reinterpret_cast<const float4*>(a.A + (size_t)min(n0 + fr[i], last) * 288 + srcoff[i]));
     };
     fetch(0);
     tprev = (uint32_t)clock();
@@ -340,7 +323,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       tgi = gi;
       if (gi > 1) mbar_wait(amfree(b), ((gi >> 1) - 1) & 1);
       tick(0);
-      aw.store(sbase + C_::OFF_AM + b * 2 * AM_BYTES, x);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t d = dst[i] + b * 2 * AM_PART;
+        sts128(d, x[i]);
+        sts128(d + AM_PART, make_float4(x[i].x - trunc_tf32(x[i].x), x[i].y - trunc_tf32(x[i].y),
+                                        x[i].z - trunc_tf32(x[i].z), x[i].w - trunc_tf32(x[i].w)));
+      }
       fence_proxy_async_smem();
       mbar_arrive(amfull(b));
       tick(1);
@@ -350,9 +339,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
     if (pt == 0) tick_flush(1);
   } else if (warp == W_TISSUE) {
     // ------------------------------------------------------------------ T GEMM issuer
-    // T of group gi + 1 is issued as soon as every worker has read T of group gi, i.e. a whole group ahead of its use
+    // T is double buffered: the blend of group gi + 1 is issued while the workers are still reading T of group gi
     if (lane == 0) {
-      const uint32_t d = tmem_base + C_::TM_T;
       const uint32_t wh = tmem_base + C_::TM_W, wl = wh + 32;
       tprev = (uint32_t)clock();
       for (int gi = 0; gi < ng; ++gi) {
@@ -360,19 +348,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         tgi = gi;
         mbar_wait(amfull(b), (gi >> 1) & 1);
         tick(0);
-        if (gi > 0) mbar_wait(tempty, (gi - 1) & 1);
+        if (gi > 1) mbar_wait(tempty(b), ((gi >> 1) - 1) & 1);
         tick(1);
         tc_fence_after();
-        const uint64_t mh0 = umma_smem_desc(sbase + C_::OFF_AM + b * 2 * AM_BYTES, 16, 1024, LAYOUT_SW128);
+        const uint32_t d = tmem_base + C_::TM_T + b * NROW;
+        // LBO = stride between n blocks, SBO = 512 (4 k rows); a k step of 8 joints = 1024 bytes
+        const uint64_t mh0 = umma_smem_desc(sbase + C_::OFF_AM + b * 2 * AM_PART, AM_BLK, 512, LAYOUT_SW128_BASE32B);
         if (!(a.ablate & 128))
 #pragma unroll
         for (int j = 0; j < 3; ++j) {  // K = 24 joints = 3 steps of 8
-          const uint64_t mh = umma_desc_advance(mh0, j * 32), ml = umma_desc_advance(mh0, AM_BYTES + j * 32);
+          const uint64_t mh = umma_desc_advance(mh0, j * 1024), ml = umma_desc_advance(mh0, AM_PART + j * 1024);
           umma_tf32_ts(d, wl + j * 8, mh, idesc, j > 0 ? 1u : 0u);
           umma_tf32_ts(d, wh + j * 8, ml, idesc, 1u);
           umma_tf32_ts(d, wh + j * 8, mh, idesc, 1u);
         }
-        umma_commit(tfull);
+        umma_commit(tfull(b));
         umma_commit(amfree(b));
         tick(2);
       }
@@ -481,21 +471,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         tma_prefetch_desc(&tmDVe);
         tma_prefetch_desc(&tmDVo);
       }
-    }
-    for (int gi = 0; gi < ng; ++gi) {
-      const int st = gi % C_::NSTAGE;
-      const uint32_t use = gi / C_::NSTAGE;
-      tgi = gi;
-      if (gi == 0) tprev = (uint32_t)clock();
-      if (use > 0) mbar_wait(sempty(st), (use - 1) & 1);
-      tick(0);
-      const uint32_t sa = sbase + C_::OFF_ST + st * C_::ST_BYTES;
-      const int n0 = group_of(gi) * FB;
-      if (a.ablate & 16) {
-        if (lane == 0) mbar_arrive(sfull(st));
-        continue;
-      }
-      if (lane == 0) {
+      tprev = (uint32_t)clock();
+      for (int gi = 0; gi < ng; ++gi) {
+        const int st = gi % C_::NSTAGE;
+        const uint32_t use = gi / C_::NSTAGE;
+        tgi = gi;
+        if (use > 0) mbar_wait(sempty(st), (use - 1) & 1);
+        tick(0);
+        const uint32_t sa = sbase + C_::OFF_ST + st * C_::ST_BYTES;
+        const int n0 = group_of(gi) * FB;
+        if (a.ablate & 16) {
+          mbar_arrive(sfull(st));
+          continue;
+        }
         mbar_arrive_expect_tx(sfull(st), C_::ST_PO_BYTES + (HAS_DV ? C_::ST_DV_TX : 0));
         tma_load_2d(sa, &tmPO, sfull(st), v0, n0 * 3);
         if (HAS_DV) {
@@ -507,16 +495,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
             tma_load_2d(sa + C_::ST_PO_BYTES + 2 * C_::DV_EBOX + h * C_::DV_OBOX_PITCH, &tmDVo, sfull(st), v0 * 3 + h * 192, ro);
           }
         }
+        tick(1);
       }
-      __syncwarp();
-      tick(1);
     }
+    __syncwarp();
   } else if (warp < NWORK) {
-    // ------------------------------------------------------------------ workers: four threads per vertex
-    // warp = 4 * (frame pair) + (TMEM lane quarter): the four warps of a quarter share one warp scheduler and one
-    // G k block and take two frames of the group each, so their barrier / TMEM latencies overlap
-    constexpr int FH = FB * 4 / NWORK;  // frames of the group per worker warp
-    static_assert(FH == 2, "two frames per worker warp");
+    // ------------------------------------------------------------------ workers: 32 / FH threads per vertex
+    // warp = 4 * (frame subset) + (TMEM lane quarter): the warps of a quarter share one warp scheduler and one G k block
+    // and take FH frames of the group each.  Fewer, fatter worker warps: the per-group fixed cost of a worker (four
+    // barrier waits, the scale exchange, address arithmetic) is paid once per FH frames, and with 18 warps per CTA every
+    // thread has 112 registers -- nothing is rematerialised.  The kernel is bound by instruction issue, not by bytes.
     const int wq = warp & 3, half = warp >> 2;
     const int kv = wq * 32 + lane;  // vertex within the tile = k row of G
     const int v = v0 + kv;
@@ -524,32 +512,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
 #pragma unroll
     for (int c = 0; c < 3; ++c) bs[c] = __ldg(a.base + c * VP + v);
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    // G addresses.  This thread owns the columns n = 24 half .. 24 half + 23 of its k row (two frames x (r, c)) in the
-    // hi part and the same + 96 in the lo part: three 16-byte chunks each (chunk i = quads 2i, 2i+1 of
-    // [f0r0, f0r1, f0r2, f1r0, f1r1, f1r2], a quad = dv_r * [p0, p1, p2, 1]).  The eight lanes of a store phase hit
-    // eight different k rows whose chunk positions are XORed with the row: all eight 16-byte slots of the 128-byte
-    // bank window, conflict free.
-    uint32_t gh[3], gl[3];
+    // G addresses.  This thread owns the columns n = 12 FH half .. + 12 FH - 1 of its k row (FH frames x (r, c)) in the
+    // hi part and the same + 96 in the lo part: 16-byte chunks of two quads each (quad = dv_r * [p0, p1, p2, 1], quads
+    // ordered [f0r0, f0r1, f0r2, f1r0, ...]).  The eight lanes of a store phase hit eight different k rows whose chunk
+    // positions are XORed with the row: all eight 16-byte slots of the 128-byte bank window, conflict free.
+    constexpr int NCH = 12 * FH / 8;
+    uint32_t gh[NCH], gl[NCH];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int nh = 24 * half + 8 * i, nl = NROW + nh;
+    for (int i = 0; i < NCH; ++i) {
+      const int nh = 12 * FH * half + 8 * i, nl = NROW + nh;
       const uint32_t row = sbase + C_::OFF_G + (kv >> 3) * 1024 + (kv & 7) * 128;
       gh[i] = row + (nh >> 6) * C_::GB_BYTES + ((((nh & 63) >> 3) ^ (kv & 7)) << 4);
       gl[i] = row + (nl >> 6) * C_::GB_BYTES + ((((nl & 63) >> 3) ^ (kv & 7)) << 4);
     }
-    auto put = [&](int i, float da, const float* pa, float db, const float* pb) {
-      uint32_t h[4], l[4];
-      split_h2(da * pa[0], da * pa[1], h[0], l[0]);
-      split_h2(da * pa[2], da, h[1], l[1]);
-      split_h2(db * pb[0], db * pb[1], h[2], l[2]);
-      split_h2(db * pb[2], db, h[3], l[3]);
-      sts128u(gh[i], h[0], h[1], h[2], h[3]);
-      sts128u(gl[i], l[0], l[1], l[2], l[3]);
-    };
     const unsigned lbit = 1u << lane;
     const float sp = a.sign_scale, sn = -a.sign_scale;
 
-    uint32_t sA = 0u, sB = 0u;  // this pair's 12 sign words (two frames), one per lane, prefetched one group ahead
+    uint32_t sA = 0u, sB = 0u;  // this warp's 6 FH sign words, one per lane, prefetched one group ahead
     auto load_signs = [&](int gi, uint32_t& w) {
       if (!HAS_SIGNS) return;
       const int n0 = group_of(gi < ng ? gi : ng - 1) * FB + half * FH;
@@ -558,16 +537,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       w = lane < FH * 6 ? __ldg(a.signs + (((size_t)n * 3 + fc % 3) * 2 + (lane & 1)) * (VP / 32) + (v >> 5)) : 0u;
     };
     const uint32_t st_po = sbase + C_::OFF_ST + (half * FH * 3) * (TILE_V * 4) + kv * 4;
-    // frames 2 half (even boxes, row half) and 2 half + 1 (odd boxes, row half)
-    const uint32_t st_dv0 = sbase + C_::OFF_ST + C_::ST_PO_BYTES + (kv >> 6) * C_::DV_EBOX + half * 768 + (kv & 63) * 12;
-    const uint32_t st_dv1 = sbase + C_::OFF_ST + C_::ST_PO_BYTES + 2 * C_::DV_EBOX + (kv >> 6) * C_::DV_OBOX_PITCH + half * 784 +
-                            (kv & 63) * 12 + 8;
+    // frame half * FH + f: row (half * FH + f) / 2 of the even (f even) or odd boxes
+    const uint32_t st_dv0 = sbase + C_::OFF_ST + C_::ST_PO_BYTES + (kv >> 6) * C_::DV_EBOX + (half * FH / 2) * 768 + (kv & 63) * 12;
+    const uint32_t st_dv1 = sbase + C_::OFF_ST + C_::ST_PO_BYTES + 2 * C_::DV_EBOX + (kv >> 6) * C_::DV_OBOX_PITCH +
+                            (half * FH / 2) * 784 + (kv & 63) * 12 + 8;
     auto body = [&](int gi, uint32_t sw, uint32_t& swn) {
       const int n0 = group_of(gi) * FB + half * FH;
+      const int b = gi & 1;
       tgi = gi;
       load_signs(gi + 1, swn);
       // ---- this group's inputs from the ring
-      float po[FH][3], dv[FH][3];
+      float p[FH][3], dv[FH][3];
       {
         const int st = gi % C_::NSTAGE;
         mbar_wait(sfull(st), (gi / C_::NSTAGE) & 1);
@@ -577,9 +557,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         for (int f = 0; f < FH; ++f)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            po[f][c] = lds32(st_po + so + (f * 3 + c) * (TILE_V * 4));
-            if (HAS_DV) {
-              dv[f][c] = lds32((f ? st_dv1 : st_dv0) + so + c * 4);  // zero beyond N and beyond vertex 6889
+            p[f][c] = lds32(st_po + so + (f * 3 + c) * (TILE_V * 4));
+            if (HAS_DV) {  // zero beyond N and beyond vertex 6889
+              dv[f][c] = lds32(((f & 1) ? st_dv1 + (f >> 1) * 784 : st_dv0 + (f >> 1) * 768) + so + c * 4);
             } else {
               dv[f][c] = 0.f;
             }
@@ -587,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         if (TIMING) {  // force the arrival
           float acc = 0.f;
           for (int f = 0; f < FH; ++f)
-            for (int c = 0; c < 3; ++c) acc += po[f][c] + dv[f][c];
+            for (int c = 0; c < 3; ++c) acc += p[f][c] + dv[f][c];
           if (acc == 1.2345e-30f) tk[7] += 1;
         }
         mbar_arrive(sempty(st));
@@ -605,63 +585,83 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
             dv[f][c] += s;
           }
       }
-      // ---- v_posed and this warp's bound on |G| of the frame pair, handed to the other three quarters
-      float p[FH][4];
+      // ---- v_posed and this warp's bound on |G| of each frame, handed to the other three quarters
 #pragma unroll
       for (int f = 0; f < FH; ++f) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) p[f][c] = bs[c] + po[f][c];
-        p[f][3] = 1.f;
+        for (int c = 0; c < 3; ++c) p[f][c] += bs[c];
         const float md = fmaxf(fmaxf(fabsf(dv[f][0]), fabsf(dv[f][1])), fabsf(dv[f][2]));
         const float mp = fmaxf(fmaxf(fabsf(p[f][0]), fabsf(p[f][1])), fmaxf(fabsf(p[f][2]), 1.f));
         // non-negative floats order like their bits
         const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(md * mp));
         if (lane == 0) sts32(scale_slot(gi, half * FH + f) + 4 * wq, __uint_as_float(mw));
       }
-      // ---- dPO = R^T dv from the T rows in TMEM
+      // ---- dPO = R^T dv from the T rows in TMEM, two frames per batch
       tick(1);
-      mbar_wait(tfull, gi & 1);
+      mbar_wait(tfull(b), (gi >> 1) & 1);
       tick(2);
       tc_fence_after();
-      uint32_t t[FH * 12];
-      const uint32_t ta = tmem_base + lane_addr + C_::TM_T + half * (FH * 12);
-      tmem_ld16(ta, t);
-      tmem_ld8(ta + 16, t + 16);
-      tmem_ld_wait();
-      tick(3);
-      tc_fence_before();
-      mbar_arrive(tempty);
       {
+        const uint32_t ta = tmem_base + lane_addr + C_::TM_T + b * NROW + half * (FH * 12);
         float* d = a.dPO + (size_t)n0 * (3 * VP) + v;
 #pragma unroll
-        for (int f = 0; f < FH; ++f) {
-          if (n0 + f <= last && !(a.ablate & 8)) {  // warp-uniform
+        for (int fb = 0; fb < FH; fb += 2) {
+          uint32_t t[24];
+          tmem_ld16(ta + fb * 12, t);
+          tmem_ld8(ta + fb * 12 + 16, t + 16);
+          tmem_ld_wait();
+          if (fb + 2 == FH) {
+            tc_fence_before();
+            mbar_arrive(tempty(b));
+          }
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-              __stcs(d + (size_t)f * (3 * VP) + c * VP,
-                     fmaf(__uint_as_float(t[f * 12 + c]), dv[f][0],
-                          fmaf(__uint_as_float(t[f * 12 + 4 + c]), dv[f][1], __uint_as_float(t[f * 12 + 8 + c]) * dv[f][2])));
+          for (int f = 0; f < 2; ++f) {
+            if (n0 + fb + f <= last && !(a.ablate & 8)) {  // warp-uniform
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                __stcs(d + (size_t)(fb + f) * (3 * VP) + c * VP,
+                       fmaf(__uint_as_float(t[f * 12 + c]), dv[fb + f][0],
+                            fmaf(__uint_as_float(t[f * 12 + 4 + c]), dv[fb + f][1],
+                                 __uint_as_float(t[f * 12 + 8 + c]) * dv[fb + f][2])));
+            }
           }
         }
       }
       tick(4);
-      // ---- the pair's scale: the four quarters have posted their maxima
+      // ---- the frames' scales: the four quarters have posted their maxima
       if (!(a.ablate & 32)) asm volatile("bar.sync %0, 128;" ::"r"(4 + half) : "memory");
-      const int E0 = scale_exponent(lds128(scale_slot(gi, half * FH))), E1 = scale_exponent(lds128(scale_slot(gi, half * FH + 1)));
-      const float s0 = __uint_as_float((uint32_t)(127 + 13 + 127 - E0) << 23);
-      const float s1 = __uint_as_float((uint32_t)(127 + 13 + 127 - E1) << 23);
-      if (wq == 0 && lane == 0)  // the drain's factor: undoes the scale and the 2^8 of W
-        sts64(inv_slot(gi) + 8 * half, __uint_as_float((uint32_t)(E0 - 13 - W_SCALE_LOG2) << 23),
-              __uint_as_float((uint32_t)(E1 - 13 - W_SCALE_LOG2) << 23));
+      float sc[FH];
+      {
+        int E[FH];
+#pragma unroll
+        for (int f = 0; f < FH; ++f) {
+          E[f] = scale_exponent(lds128(scale_slot(gi, half * FH + f)));
+          sc[f] = __uint_as_float((uint32_t)(127 + 13 + 127 - E[f]) << 23);
+        }
+        if (wq == 0 && lane == 0) {  // the drain's factors: undo the scale and the 2^8 of W
+#pragma unroll
+          for (int f = 0; f < FH; f += 2)
+            sts64(inv_slot(gi) + 4 * (half * FH + f), __uint_as_float((uint32_t)(E[f] - 13 - W_SCALE_LOG2) << 23),
+                  __uint_as_float((uint32_t)(E[f + 1] - 13 - W_SCALE_LOG2) << 23));
+        }
+      }
       // ---- G for the dA GEMM (the previous group's MMAs over this k block must have finished reading it)
       if (gi > 0) mbar_wait(gfree(wq), (gi - 1) & 1);
       tick(5);
       if (!(a.ablate & 2)) {
-        const float d0[3] = {dv[0][0] * s0, dv[0][1] * s0, dv[0][2] * s0};
-        const float d1[3] = {dv[1][0] * s1, dv[1][1] * s1, dv[1][2] * s1};
-        put(0, d0[0], p[0], d0[1], p[0]);
-        put(1, d0[2], p[0], d1[0], p[1]);
-        put(2, d1[1], p[1], d1[2], p[1]);
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {  // chunk i = quads 2i, 2i + 1; quad qd = (frame qd / 3, row qd % 3)
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int qd = 2 * i + e, f = qd / 3, r = qd % 3;
+            const float ds = dv[f][r] * sc[f];
+            split_h2(ds * p[f][0], ds * p[f][1], h[2 * e], l[2 * e]);
+            split_h2(ds * p[f][2], ds, h[2 * e + 1], l[2 * e + 1]);
+          }
+          sts128u(gh[i], h[0], h[1], h[2], h[3]);
+          sts128u(gl[i], l[0], l[1], l[2], l[3]);
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(gfull(wq));
@@ -711,7 +711,7 @@ int launch_timing(const Maps& m, Args a, cudaStream_t s) {
   NB_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
   const double groups = (double)NT_V * cdiv(a.N, FB);
   static const char* names[4][8] = {
-      {"ring LDS", "signs + max", "wait tfull", "tmem ld", "dPO", "scale + wait gfree", "G phase", "wait sfull"},
+      {"ring LDS", "signs + max", "wait tfull", "-", "tmem ld + dPO", "scale + wait gfree", "G phase", "wait sfull"},
       {"wait amfree", "Amat store", "fetch", "-", "-", "-", "-", "-"},
       {"wait gfull0", "wait gfull1", "wait gfull2", "wait gfull3", "mma0", "mma1", "mma2", "mma3"},
       {"wait d2full", "wait slab free", "copy + sum", "bulk reduce", "-", "-", "-", "-"}};
@@ -725,7 +725,7 @@ int launch_timing(const Maps& m, Args a, cudaStream_t s) {
   // event trace of CTA TRACE_CTA (clock of its SM), groups 8..13: one line per (role warp, group)
   static uint32_t tr[TRACE_WORDS];
   NB_CUDA(cudaMemcpy(tr, trace, sizeof(tr), cudaMemcpyDeviceToHost));
-  const int show[] = {0, 3, 12, 15, W_PROD_, W_ISSUE_, W_DRAIN_, W_DRAIN_ + 3, W_LOAD_, W_TISSUE_};
+  const int show[] = {0, 3, W_PROD_ - 4, W_PROD_ - 1, W_PROD_, W_ISSUE_, W_DRAIN_, W_DRAIN_ + 3, W_LOAD_, W_TISSUE_};
   const uint32_t t0 = tr[(W_LOAD_ * TRACE_NG + 8) * 8 + 0];
   for (int w : show)
     for (int g = 8; g < 14; ++g) {

@@ -14,12 +14,15 @@
 //     load, two 16-byte stores: raw fp32 as the hi part, x - trunc(x) as the lo part) instead of scalars;
 //   * T and Amat are single buffered: the other CTA of the SM fills the tensor pipe meanwhile.
 // Roles per CTA (9 warps): 4 workers (thread = vertex = TMEM lane), 3 Amat writers, the MMA issuer, the loader that
-// keeps a 2-stage bulk-async ring of pose offsets (16 slots x 3 components x 512 bytes per stage) in flight.
-#ifndef NB_MBAR_SLEEP
-#define NB_MBAR_SLEEP 32
+// keeps a 2-stage ring of pose offsets (16 slots x 3 components x 512 bytes per stage) in flight -- ONE TMA tensor copy
+// per mesh and stage (box 128 vertices x 48 or 24 rows of the (N*3, VP) matrix; rows beyond N land as zeros): a bulk
+// copy per row cost the loader warp ~125 cycles each, 6 000 cycles per group, which was the period of the kernel.
+#ifndef NB_MBAR_SUSPEND_NS
+#define NB_MBAR_SUSPEND_NS 1000000
 #endif
 #include "common.cuh"
 #include "sm100.cuh"
+#include "tmap.cuh"
 
 using namespace nb;
 using namespace nb::sm100;
@@ -67,7 +70,8 @@ struct Args {
 // MODE 0: one mesh, 16 frames per group, vertices written.
 // MODE 1: fused L1 of two meshes (slots 0-7 = mesh a, 8-15 = mesh b: 8 frames per group), sign bits written.
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const Args a) {
+__global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant__ CUtensorMap tmPO,
+                                                          const __grid_constant__ CUtensorMap tmPO2, const Args a) {
   constexpr int FG = MODE == 0 ? SL : SL / 2;  // frames per group
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -165,24 +169,21 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const Args a) {
       if (gi + 1 < ng) fetch(gi + 1);
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ loader: 48 bulk copies of 512 bytes per group
-    for (int gi = 0; gi < ng; ++gi) {
-      const int st = gi & 1;
-      if (gi >= 2) mbar_wait(sempty(st), ((gi >> 1) - 1) & 1);
-      if (lane == 0) mbar_arrive_expect_tx(sfull(st), ST_BYTES);
-      __syncwarp();
-      const int n0 = group_of(gi) * FG;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int e = lane + 32 * h;  // (slot, component)
-        if (e < SL * 3) {
-          const int s = e / 3, c = e % 3;
-          const float* P = (MODE == 1 && s >= FG) ? a.PO2 : a.PO;
-          bulk_g2s(sbase + OFF_ST + st * ST_BYTES + e * (TILE_V * 4),
-                   P + (size_t)slot_frame(n0, s) * (3 * VP) + c * VP + v0, TILE_V * 4, sfull(st));
-        }
+    // ------------------------------------------------------------------ loader
+    if (lane == 0) {
+      tma_prefetch_desc(&tmPO);
+      if (MODE == 1) tma_prefetch_desc(&tmPO2);
+      for (int gi = 0; gi < ng; ++gi) {
+        const int st = gi & 1;
+        if (gi >= 2) mbar_wait(sempty(st), ((gi >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(sfull(st), ST_BYTES);
+        const int n0 = group_of(gi) * FG;
+        const uint32_t dst = sbase + OFF_ST + st * ST_BYTES;
+        tma_load_2d(dst, &tmPO, sfull(st), v0, n0 * 3);
+        if (MODE == 1) tma_load_2d(dst + ST_BYTES / 2, &tmPO2, sfull(st), v0, n0 * 3);
       }
     }
+    __syncwarp();
   } else if (warp == 7) {
     // ------------------------------------------------------------------ T GEMM issuer
     if (lane == 0) {
@@ -315,7 +316,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const Args a) {
 template <int MODE>
 int launch(const Args& a, cudaStream_t s) {
   NB_SET_SMEM_ONCE(k_skin_fwd2<MODE>, SMEM_BYTES);
-  k_skin_fwd2<MODE><<<NT_V * a.nchunks, THREADS, SMEM_BYTES, s>>>(a);
+  constexpr int ROWS = MODE == 0 ? SL * 3 : SL * 3 / 2;  // box rows per copy
+  CUtensorMap m1, m2;
+  if (int rc = make_tmap_2d(&m1, a.PO, 4, VP, (uint64_t)a.N * 3, (uint64_t)VP * 4, TILE_V, ROWS)) return rc;
+  m2 = m1;
+  if (MODE == 1)
+    if (int rc = make_tmap_2d(&m2, a.PO2, 4, VP, (uint64_t)a.N * 3, (uint64_t)VP * 4, TILE_V, ROWS)) return rc;
+  k_skin_fwd2<MODE><<<NT_V * a.nchunks, THREADS, SMEM_BYTES, s>>>(m1, m2, a);
   NB_LAUNCH_CHECK("skin_fwd2");
 }
 

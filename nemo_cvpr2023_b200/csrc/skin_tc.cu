@@ -962,7 +962,7 @@ extern "C" int nemo_b200_skin_fwd(const float* A, const float* PO, const float* 
                                   void* stream) {
   if (N == 0) return 0;
   NB_REQUIRE(A && PO && base && Wt && V && N >= 0, "skin_fwd: bad args");
-  if (fwd_generation() >= 2) return nb::skin_fwd2(A, PO, base, Wt, V, N, S(stream));
+  if (fwd_generation() >= 2 && ((uintptr_t)PO & 15) == 0) return nb::skin_fwd2(A, PO, base, Wt, V, N, S(stream));
   SkinArgs a{};
   a.A = A; a.PO = PO; a.base = base; a.Wt = Wt; a.V = V; a.N = N;
   chunking(N, FB, 2, 2.0, 32, a.groups_per_chunk, a.nchunks);
@@ -974,7 +974,8 @@ extern "C" int nemo_b200_skin_l1_fwd(const float* A_a, const float* PO_a, const 
                                      void* stream) {
   if (N == 0) return 0;
   NB_REQUIRE(A_a && PO_a && A_b && PO_b && base && Wt && signs && l1_sum && N >= 0, "skin_l1_fwd: bad args");
-  if (fwd_generation() >= 2) return nb::skin_l1_fwd2(A_a, PO_a, A_b, PO_b, base, Wt, signs, l1_sum, N, S(stream));
+  if (fwd_generation() >= 2 && (((uintptr_t)PO_a | (uintptr_t)PO_b) & 15) == 0)
+    return nb::skin_l1_fwd2(A_a, PO_a, A_b, PO_b, base, Wt, signs, l1_sum, N, S(stream));
   SkinArgs a{};
   a.A = A_a; a.PO = PO_a; a.A2 = A_b; a.PO2 = PO_b; a.base = base; a.Wt = Wt; a.signs = signs; a.l1_sum = l1_sum;
   a.N = N;
