@@ -156,7 +156,7 @@ struct Args {
   int N, groups_per_chunk, nchunks;
   unsigned long long* dbg;  // TIMING instantiation only: per-role phase cycle counters
   uint32_t* trace;
-  // debug (NEMO_B200_SKIN_ABLATE): 1 no dA reductions, 2 no G stores, 4 no dA MMAs, 8 no dPO stores, 16 no loads,
+  // debug (NEMO_B200_SKIN_ABLATE, with NEMO_B200_SKIN_TIMING=1): 1 no dA reductions, 2 no G stores, 4 no dA MMAs, 8 no dPO stores, 16 no loads,
   // 32 no scale exchange, 64 no accumulator drain, 128 no T MMAs
   int ablate;
 };
@@ -188,19 +188,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       for (int i = 0; i < 8; ++i) atomicAdd(a.dbg + role * 8 + i, (unsigned long long)tk[i]);
   };
   using C_ = Cfg;
+  const int abl = TIMING ? a.ablate : 0;  // ablation switches exist in the instrumented instantiation only
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = sbase + C_::OFF_BARS;
   auto tfull = [&](int b) { return bars + 8u * b; };            // T[b] complete                     (commit)
   auto tempty = [&](int b) { return bars + 8u * (28 + b); };    // T[b] read by the workers          (all worker threads)
   auto amfree = [&](int b) { return bars + 8u * (2 + b); };     // T GEMM done reading Amat[b]       (commit)
-  auto amfull = [&](int b) { return bars + 8u * (26 + b); };    // Amat[b] written                   (96)
+  auto amfull = [&](int b) { return bars + 8u * (26 + b); };    // Amat[b] written                   (3 warps)
   auto d2full = [&](int b) { return bars + 8u * (4 + b); };     // dA[b] complete                    (commit)
   auto d2empty = [&](int b) { return bars + 8u * (6 + b); };    // dA[b] copied to the slabs         (256)
   auto gfull = [&](int kb) { return bars + 8u * (8 + kb); };    // G k block written                 (128)
   auto gfree = [&](int kb) { return bars + 8u * (12 + kb); };   // dA GEMM done reading the k block  (commit)
   auto sfull = [&](int st) { return bars + 8u * (16 + st); };   // input stage landed                (tx bytes)
-  auto sempty = [&](int st) { return bars + 8u * (20 + st); };  // input stage read by the workers   (512)
+  auto sempty = [&](int st) { return bars + 8u * (20 + st); };  // input stage read by the workers   (warps)
   const uint32_t tmem_slot = bars + 8u * 24;
   static_assert(C_::NSTAGE <= 4, "barrier slots above");
   auto scale_slot = [&](int gi, int f) { return sbase + C_::OFF_SC + (uint32_t)(((gi & 3) * FB + f) * 16); };
@@ -220,19 +221,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
-      mbar_init(tempty(b), NWORK * 32);
+      mbar_init(tempty(b), NWORK);
       mbar_init(amfree(b), 1);
-      mbar_init(amfull(b), 96);
+      mbar_init(amfull(b), 3);
       mbar_init(d2full(b), 1);
-      mbar_init(d2empty(b), 128);
+      mbar_init(d2empty(b), 4);
     }
     for (int kb = 0; kb < 4; ++kb) {
-      mbar_init(gfull(kb), NWORK * 8);
+      mbar_init(gfull(kb), NWORK / 4);
       mbar_init(gfree(kb), 1);
     }
     for (int st = 0; st < C_::NSTAGE; ++st) {
       mbar_init(sfull(st), 1);
-      mbar_init(sempty(st), NWORK * 32);
+      mbar_init(sempty(st), NWORK);
     }
     fence_barrier_init();
   }
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
                                         x[i].z - trunc_tf32(x[i].z), x[i].w - trunc_tf32(x[i].w)));
       }
       fence_proxy_async_smem();
-      mbar_arrive(amfull(b));
+      mbar_arrive_warp(amfull(b));
       tick(1);
       if (gi + 1 < ng) fetch(gi + 1);
       tick(2);
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         const uint32_t d = tmem_base + C_::TM_T + b * NROW;
         // LBO = stride between n blocks, SBO = 512 (4 k rows); a k step of 8 joints = 1024 bytes
         const uint64_t mh0 = umma_smem_desc(sbase + C_::OFF_AM + b * 2 * AM_PART, AM_BLK, 512, LAYOUT_SW128_BASE32B);
-        if (!(a.ablate & 128))
+        if (!(abl & 128))
 #pragma unroll
         for (int j = 0; j < 3; ++j) {  // K = 24 joints = 3 steps of 8
           const uint64_t mh = umma_desc_advance(mh0, j * 1024), ml = umma_desc_advance(mh0, AM_PART + j * 1024);
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
           tick(kb);
           if (kb == 0 && use > 0) mbar_wait(d2empty(b), (use - 1) & 1);
           tc_fence_after();
-          if (!(a.ablate & 4))
+          if (!(abl & 4))
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)
             umma_f16_ts(d, wt + boff + kb * 16 + ks * 8, umma_desc_advance(gh0, (kb * 2 + ks) * 2048), idesc_d,
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       const float4 iv0 = lds128(inv_slot(gi)), iv1 = lds128(inv_slot(gi) + 16);
       const float inv8[FB] = {iv0.x, iv0.y, iv0.z, iv0.w, iv1.x, iv1.y, iv1.z, iv1.w};
       const uint32_t srow = slab + (6 * q + jl) * 48 + c2 * 4;
-      if (!(a.ablate & 64))
+      if (!(abl & 64))
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {  // 32 columns of each half per batch
         uint32_t x[16], y[16];
@@ -450,11 +451,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(d2empty(b));
+      mbar_arrive_warp(d2empty(b));
       tick(2);
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, 128;" ::: "memory");  // slab complete
-      if (dt == 0 && !(a.ablate & 1)) {
+      if (dt == 0 && !(abl & 1)) {
         const int n0 = group_of(gi) * FB;
         bulk_reduce_add_f32(a.dA + (size_t)n0 * 288, slab, (uint32_t)min(FB, a.N - n0) * 1152u);
         bulk_commit();
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         tick(0);
         const uint32_t sa = sbase + C_::OFF_ST + st * C_::ST_BYTES;
         const int n0 = group_of(gi) * FB;
-        if (a.ablate & 16) {
+        if (abl & 16) {
           mbar_arrive(sfull(st));
           continue;
         }
@@ -529,9 +530,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
     const float sp = a.sign_scale, sn = -a.sign_scale;
 
     uint32_t sA = 0u, sB = 0u;  // this warp's 6 FH sign words, one per lane, prefetched one group ahead
-    auto load_signs = [&](int gi, uint32_t& w) {
+    auto load_signs = [&](int g, uint32_t& w) {
       if (!HAS_SIGNS) return;
-      const int n0 = group_of(gi < ng ? gi : ng - 1) * FB + half * FH;
+      const int n0 = g * FB + half * FH;
       const int fc = lane >> 1;  // word (f*3 + c)*2 + {pos, neg}
       const int n = min(n0 + fc / 3, last);
       w = lane < FH * 6 ? __ldg(a.signs + (((size_t)n * 3 + fc % 3) * 2 + (lane & 1)) * (VP / 32) + (v >> 5)) : 0u;
@@ -541,16 +542,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
     const uint32_t st_dv0 = sbase + C_::OFF_ST + C_::ST_PO_BYTES + (kv >> 6) * C_::DV_EBOX + (half * FH / 2) * 768 + (kv & 63) * 12;
     const uint32_t st_dv1 = sbase + C_::OFF_ST + C_::ST_PO_BYTES + 2 * C_::DV_EBOX + (kv >> 6) * C_::DV_OBOX_PITCH +
                             (half * FH / 2) * 784 + (kv & 63) * 12 + 8;
-    auto body = [&](int gi, uint32_t sw, uint32_t& swn) {
-      const int n0 = group_of(gi) * FB + half * FH;
+    // g = this group, gn = the next one in the rotated walk (= g at the end); st / sph = ring stage and its phase
+    auto body = [&](int gi, int g, int gn, int st, uint32_t sph, uint32_t sw, uint32_t& swn) {
+      const int n0 = g * FB + half * FH;
       const int b = gi & 1;
       tgi = gi;
-      load_signs(gi + 1, swn);
+      load_signs(gn, swn);
       // ---- this group's inputs from the ring
       float p[FH][3], dv[FH][3];
       {
-        const int st = gi % C_::NSTAGE;
-        mbar_wait(sfull(st), (gi / C_::NSTAGE) & 1);
+        mbar_wait(sfull(st), sph);
         tick(7);
         const uint32_t so = st * C_::ST_BYTES;
 #pragma unroll
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
             for (int c = 0; c < 3; ++c) acc += p[f][c] + dv[f][c];
           if (acc == 1.2345e-30f) tk[7] += 1;
         }
-        mbar_arrive(sempty(st));
+        mbar_arrive_warp(sempty(st));
       }
       tick(0);
       // ---- upstream gradient of the vertex in each frame
@@ -612,11 +613,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
           tmem_ld_wait();
           if (fb + 2 == FH) {
             tc_fence_before();
-            mbar_arrive(tempty(b));
+            mbar_arrive_warp(tempty(b));
           }
 #pragma unroll
           for (int f = 0; f < 2; ++f) {
-            if (n0 + fb + f <= last && !(a.ablate & 8)) {  // warp-uniform
+            if (n0 + fb + f <= last && !(abl & 8)) {  // warp-uniform
 #pragma unroll
               for (int c = 0; c < 3; ++c)
                 __stcs(d + (size_t)(fb + f) * (3 * VP) + c * VP,
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       }
       tick(4);
       // ---- the frames' scales: the four quarters have posted their maxima
-      if (!(a.ablate & 32)) asm volatile("bar.sync %0, 128;" ::"r"(4 + half) : "memory");
+      if (!(abl & 32)) asm volatile("bar.sync %0, 128;" ::"r"(4 + half) : "memory");
       float sc[FH];
       {
         int E[FH];
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       // ---- G for the dA GEMM (the previous group's MMAs over this k block must have finished reading it)
       if (gi > 0) mbar_wait(gfree(wq), (gi - 1) & 1);
       tick(5);
-      if (!(a.ablate & 2)) {
+      if (!(abl & 2)) {
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {  // chunk i = quads 2i, 2i + 1; quad qd = (frame qd / 3, row qd % 3)
           uint32_t h[4], l[4];
@@ -664,14 +665,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(gfull(wq));
+      mbar_arrive_warp(gfull(wq));
       tick(6);
     };
-    load_signs(0, sA);
+    int g = group_of(0), st = 0;
+    uint32_t sph = 0;
+    auto next_group = [&](int x) { return x + 1 == g_begin + ng ? g_begin : x + 1; };
+    auto advance = [&]() {
+      g = next_group(g);
+      if (++st == C_::NSTAGE) st = 0, sph ^= 1u;
+    };
+    load_signs(g, sA);
     tprev = (uint32_t)clock();
     for (int gi = 0; gi < ng; gi += 2) {
-      body(gi, sA, sB);
-      if (gi + 1 < ng) body(gi + 1, sB, sA);
+      body(gi, g, gi + 1 < ng ? next_group(g) : g, st, sph, sA, sB);
+      advance();
+      if (gi + 1 < ng) {
+        body(gi + 1, g, gi + 2 < ng ? next_group(g) : g, st, sph, sB, sA);
+        advance();
+      }
     }
     tick_flush(0);
   }

@@ -97,12 +97,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
 
   if (tid == 0) {
     mbar_init(tfull, 1);
-    mbar_init(tempty, 128);
-    mbar_init(amfull, 96);
+    mbar_init(tempty, 4);
+    mbar_init(amfull, 3);
     mbar_init(amfree, 1);
     for (int st = 0; st < 2; ++st) {
       mbar_init(sfull(st), 1);
-      mbar_init(sempty(st), 128);
+      mbar_init(sempty(st), 4);
     }
     fence_barrier_init();
   }
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
                                              x[i].z - trunc_tf32(x[i].z), x[i].w - trunc_tf32(x[i].w)));
       }
       fence_proxy_async_smem();
-      mbar_arrive(amfull);
+      mbar_arrive_warp(amfull);
       if (gi + 1 < ng) fetch(gi + 1);
     }
   } else if (warp == 8) {
@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
           batch(ring, 4 * b, o);
           if (b == 3) {  // the last reads of T and of the ring stage are done
             tc_fence_before();
-            mbar_arrive(tempty);
-            mbar_arrive(sempty(st));
+            mbar_arrive_warp(tempty);
+            mbar_arrive_warp(sempty(st));
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
           batch(ring, FG + 4 * b, ob);   // mesh b, same frames
           if (b == 1) {
             tc_fence_before();
-            mbar_arrive(tempty);
-            mbar_arrive(sempty(st));
+            mbar_arrive_warp(tempty);
+            mbar_arrive_warp(sempty(st));
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
