@@ -189,6 +189,12 @@ def fold_vposer(sd, device):
 
 _NVTX = bool(int(__import__('os').environ.get('NEMO_B200_NVTX', '0')))
 _DP_DRY = bool(int(__import__('os').environ.get('NEMO_B200_DP_DRY', '0')))
+# experimental (NEMO_B200_DP_GRAPH_NCCL=1): data-parallel steps as ONE CUDA graph with the bucketed NCCL all-reduces
+# captured on the communication stream.  Measured on 2 GPUs: no gain (2.073 vs 2.076 ms/step -- the compute kernels are
+# persistent, one CTA per SM with ~200 KB of shared memory, so an NCCL kernel only becomes resident between them and the
+# ~50 us of the 9 MB all-reduce stay exposed either way), and the capture hung the 2-rank parity test once.  Default 0:
+# two graphs around one eager all-reduce.
+_DP_GRAPH_NCCL = bool(int(__import__('os').environ.get('NEMO_B200_DP_GRAPH_NCCL', '0')))
 
 
 class _Range:
@@ -738,7 +744,8 @@ class FitEngine:
         plateau scheduler that changes one simply causes a re-capture) runs eagerly, the second captures, later ones
         replay.  The indices are copied into their fixed workspace slots outside the graph.  Under data parallelism NCCL
         stays outside the graphs: graph 1 = forward + backward, ONE eager all-reduce of the shared gradient, graph 2 = the
-        optimisers (the bucketed, overlapped all-reduce belongs to the eager `forward_backward`).  Not used when
+        optimisers (the bucketed, overlapped all-reduce belongs to the eager `forward_backward`;
+        NEMO_B200_DP_GRAPH_NCCL=1 captures it instead -- experimental, see the top of the file).  Not used when
         per-entry-point profiling is on."""
         N = int(view_idx.shape[0])
         w = self.ws(N)
@@ -749,7 +756,7 @@ class FitEngine:
         key = (N, mode, bool(detach_pose), bool(self.training), bool(skip_lag), bool(self.compute_betas_grad),
                tuple((id(g), g.lr, g.wd, g.betas, g.eps, g.decoupled) for g in groups))
 
-        dp = self.world > 1
+        dp = self.world > 1 and not (_DP_GRAPH_NCCL and self.dp_overlap and not self.dp_defer)
 
         def body():
             # data parallel: the graph stops before the all-reduce (NCCL stays OUTSIDE the captured graphs: one eager
@@ -761,7 +768,7 @@ class FitEngine:
                                             _indices_loaded=True)
             finally:
                 self.dp_defer = saved
-            if not dp:
+            if not dp:      # one GPU, or the collectives are part of the graph (forward_backward has joined them)
                 self.optimizer_step(groups, skip_lag=skip_lag)
             return out
 
