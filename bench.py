@@ -466,14 +466,14 @@ def _run_gpu(a, rank, local, world, dev):
                 'd2h_bytes_per_step': A * 9 * 4, 'ms_per_step': t_e2e / a.steps * 1e3},
         'gpu_launches': int(kernels.get('kernels', launches)),
         'gpu_launches_detail': dict(kernels, repo_c_abi_count=int(launches)),
-        'roofline': {'bound': 'hbm', 'kernel': 'k_skin_tc_fwd<0> + k_skin_tc_bwd<dV> (K7, vertices written, dV read: 5 streams/frame)',
+        'roofline': {'bound': 'hbm', 'kernel': 'k_skin_fwd2<0> + k_skin_bwd2<dV> (K7, vertices written, dV read: 5 streams/frame)',
                      'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
                      'algorithmic_bytes_per_launch_pair': alg, 'frames_per_launch': nK7,
                      'fwd_ms': tk['fwd'] * 1e3, 'bwd_ms': tk['bwd'] * 1e3,
                      'fwd_frac': 2 * STREAM_BYTES * nK7 / tk['fwd'] / 1e9 / peak,
                      'bwd_frac': 3 * STREAM_BYTES * nK7 / tk['bwd'] / 1e9 / peak,
-                     'in_step': {'kernel': 'k_skin_tc_fwd<1> (fused L1 of two meshes) + k_skin_tc_bwd<signs>: the variants '
+                     'in_step': {'kernel': 'k_skin_fwd2<1> (fused L1 of two meshes) + k_skin_bwd2<signs>: the variants '
                                            'the timed step launches, 4 streams/frame',
                                  'achieved': in_step, 'frac': in_step / peak, 'algorithmic_bytes_per_launch_pair': alg_in,
                                  'l1_fwd_ms': tk['l1_fwd'] * 1e3, 'bwd_signs_ms': tk['bwd_signs'] * 1e3}},

@@ -30,6 +30,9 @@
 #include <mutex>
 #include <array>
 #include "common.cuh"
+#ifndef NB_MBAR_SUSPEND_NS
+#define NB_MBAR_SUSPEND_NS 1000000  // waiting warps are parked by the hardware instead of spinning on try_wait
+#endif
 #include "sm100.cuh"
 
 using namespace nb;

@@ -137,7 +137,7 @@ struct Cfg {
   static constexpr int OFF_SC = OFF_STG + 2 * STG_BYTES;  // max |G|: [group & 3][frame][lane quarter]
   static constexpr int OFF_INV = OFF_SC + 512;            // the drain's factor per frame: [group & 3][frame]
   static constexpr int OFF_BARS = OFF_INV + 128;
-  static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
+  static constexpr int SMEM_BYTES = OFF_BARS + 512 + 1024;
   static constexpr int TM_T = 0;        // T: 2 x 96 columns (double buffered: the blend of the next group runs ahead)
   static constexpr int TM_WT = 192;     // [W_hi^T ; W_lo^T] fp16: 64 columns (k = vertex, two per column)
   static constexpr int TM_D = 256;      // dA: 192 columns [. G_hi | . G_lo], TWO M = 64 accumulators (lane offsets 0 / 16)
@@ -153,6 +153,9 @@ struct Args {
   const float* dV; const uint32_t* signs;
   float* dPO; float* dA;
   float sign_scale;
+  // signs only (no dV): |G| = sign_scale * |[p;1]| needs no per-frame maximum -- one power of two takes
+  // sign_scale to (32, 64], which keeps every vertex coordinate below ~1000 m inside the fp16 range
+  float sc_static, inv_static;
   int N, groups_per_chunk, nchunks;
   unsigned long long* dbg;  // TIMING instantiation only: per-role phase cycle counters
   uint32_t* trace;
@@ -204,6 +207,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
   auto sempty = [&](int st) { return bars + 8u * (20 + st); };  // input stage read by the workers   (warps)
   const uint32_t tmem_slot = bars + 8u * 24;
   static_assert(C_::NSTAGE <= 4, "barrier slots above");
+  // the four quarters of a frame subset have posted their maxima of group gi                          (4 warps)
+  auto scposted = [&](int gi, int half) { return bars + 8u * (32 + (gi & 3) * 4 + half); };
   auto scale_slot = [&](int gi, int f) { return sbase + C_::OFF_SC + (uint32_t)(((gi & 3) * FB + f) * 16); };
   auto inv_slot = [&](int gi) { return sbase + C_::OFF_INV + (uint32_t)((gi & 3) * FB * 4); };
 
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       mbar_init(gfull(kb), NWORK / 4);
       mbar_init(gfree(kb), 1);
     }
+    for (int i = 0; i < 16; ++i) mbar_init(bars + 8u * (32 + i), 4);
     for (int st = 0; st < C_::NSTAGE; ++st) {
       mbar_init(sfull(st), 1);
       mbar_init(sempty(st), NWORK);
@@ -298,13 +304,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
 
   if (warp >= W_PROD && warp < W_ISSUE) {
     // ------------------------------------------------------------------ Amat writers (double buffered)
-    // float4 unit u = pt + 96 i of the group's 8 x 72: frame u / 72, joint (u % 72) / 3, quarter u % 3
+    // float4 unit u = pt + 96 i of the group's 24 joints x 24 quads (quad = frame * 3 + quarter of the 3x4 transform):
+    // eight consecutive lanes take eight consecutive quads of ONE joint, i.e. the eight 16-byte slots of one 128-byte
+    // k row (in swizzled order): the 16-byte stores of a phase are conflict free
     const int pt = tid - W_PROD * 32;
     uint32_t dst[6];
     int srcoff[6], fr[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const int u = pt + 96 * i, f = u / 72, j = (u % 72) / 3, q = u % 3;
+      const int u = pt + 96 * i, j = (u >> 3) % 24, gq = ((u >> 3) / 24) * 8 + (u & 7), f = gq / 3, q = gq % 3;
       const int n = f * 12 + 4 * q, nb = n >> 5, np = n & 31;
       dst[i] = sbase + C_::OFF_AM + nb * AM_BLK + j * 128 + ((((np >> 3) ^ j) & 3) << 5) + ((np >> 2) & 1) * 16;
       srcoff[i] = j * 12 + 4 * q;
@@ -428,8 +436,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       }
       tick(1);
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32 + 16 * b) << 16) + C_::TM_D;
-      const float4 iv0 = lds128(inv_slot(gi)), iv1 = lds128(inv_slot(gi) + 16);
-      const float inv8[FB] = {iv0.x, iv0.y, iv0.z, iv0.w, iv1.x, iv1.y, iv1.z, iv1.w};
+      float inv8[FB];
+      if (HAS_DV) {
+        const float4 iv0 = lds128(inv_slot(gi)), iv1 = lds128(inv_slot(gi) + 16);
+        inv8[0] = iv0.x, inv8[1] = iv0.y, inv8[2] = iv0.z, inv8[3] = iv0.w;
+        inv8[4] = iv1.x, inv8[5] = iv1.y, inv8[6] = iv1.z, inv8[7] = iv1.w;
+      } else {
+#pragma unroll
+        for (int f = 0; f < FB; ++f) inv8[f] = a.inv_static;
+      }
       const uint32_t srow = slab + (6 * q + jl) * 48 + c2 * 4;
       if (!(abl & 64))
 #pragma unroll
@@ -591,12 +606,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       for (int f = 0; f < FH; ++f) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) p[f][c] += bs[c];
+        if (!HAS_DV) continue;  // static scale
         const float md = fmaxf(fmaxf(fabsf(dv[f][0]), fabsf(dv[f][1])), fabsf(dv[f][2]));
         const float mp = fmaxf(fmaxf(fabsf(p[f][0]), fabsf(p[f][1])), fmaxf(fabsf(p[f][2]), 1.f));
         // non-negative floats order like their bits
         const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(md * mp));
         if (lane == 0) sts32(scale_slot(gi, half * FH + f) + 4 * wq, __uint_as_float(mw));
       }
+      // posted: an arrival, not a rendezvous -- the other quarters only need this warp to have come THIS far, and they
+      // look a whole dPO phase later
+      if (HAS_DV) mbar_arrive_warp(scposted(gi, half));
       // ---- dPO = R^T dv from the T rows in TMEM, two frames per batch
       tick(1);
       mbar_wait(tfull(b), (gi >> 1) & 1);
@@ -630,9 +649,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_skin_bwd2(const __grid_constant_
       }
       tick(4);
       // ---- the frames' scales: the four quarters have posted their maxima
-      if (!(abl & 32)) asm volatile("bar.sync %0, 128;" ::"r"(4 + half) : "memory");
       float sc[FH];
-      {
+      if (!HAS_DV) {
+#pragma unroll
+        for (int f = 0; f < FH; ++f) sc[f] = a.sc_static;
+      } else {
+        mbar_wait(scposted(gi, half), (gi >> 2) & 1);
         int E[FH];
 #pragma unroll
         for (int f = 0; f < FH; ++f) {
@@ -762,6 +784,14 @@ int skin_bwd2(const float* A, const float* PO, const float* base, const float* W
   skin_chunking(N, FB, 1, 2.0, 16, a.groups_per_chunk, a.nchunks);
   static const int abl = [] { const char* e = getenv("NEMO_B200_SKIN_ABLATE"); return e ? atoi(e) : 0; }();
   a.ablate = abl;
+  {
+    int e = 0;
+    const float ss = fabsf(sign_scale);
+    if (ss > 0.f && isfinite(ss)) frexpf(ss, &e);      // ss = m 2^e, m in [0.5, 1): ss 2^(6 - e) in [32, 64)
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    a.sc_static = ldexpf(1.f, 6 - e);
+    a.inv_static = ldexpf(1.f, e - 6 - W_SCALE_LOG2);
+  }
   Maps m;
   if (int rc = make_tmap_2d(&m.po, PO, 4, VP, (uint64_t)N * 3, (uint64_t)VP * 4, TILE_V, FB * 3)) return rc;
   m.dve = m.dvo = m.po;

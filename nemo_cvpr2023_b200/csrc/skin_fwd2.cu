@@ -134,13 +134,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
 
   if (warp >= 4 && warp < 7) {
     // ------------------------------------------------------------------ Amat writers (96 threads)
-    // float4 unit u = pt + 96 i of the group's 16 x 72: slot u / 72, joint (u % 72) / 3, quarter u % 3
+    // float4 unit u = pt + 96 i of the group's 24 joints x 48 quads (quad = slot * 3 + quarter of the 3x4 transform):
+    // eight consecutive lanes take eight consecutive quads of ONE joint, i.e. the eight 16-byte slots of one 128-byte
+    // k row (in swizzled order): the 16-byte stores of a phase are conflict free
     const int pt = tid - 128;
     uint32_t dst[12];
     int srcoff[12], sl[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-      const int u = pt + 96 * i, s = u / 72, j = (u % 72) / 3, q = u % 3;
+      const int u = pt + 96 * i, j = (u >> 3) % 24, gq = ((u >> 3) / 24) * 8 + (u & 7), s = gq / 3, q = gq % 3;
       const int n = s * 12 + 4 * q, nb = n >> 5, np = n & 31;
       dst[i] = sbase + OFF_AM + nb * AM_BLK + j * 128 + ((((np >> 3) ^ j) & 3) << 5) + ((np >> 2) & 1) * 16;
       srcoff[i] = j * 12 + 4 * q;

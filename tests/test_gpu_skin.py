@@ -117,7 +117,7 @@ def test_fused_l1_and_sign_backward(ctx, N):
     vb, _, _ = _ref_skin(A2, PO2, sm)
     ref = np.abs(va - vb).sum()
     assert abs(float(l1) - ref) <= 1e-5 * ref, (float(l1), ref)
-    scale = 0.37
+    scale = {1: 0.37, 5: 3.0e-7, 36: 2500.0, 131: 0.37}[N]   # the signs-only backward scales its fp16 operands statically
     dPO = torch.empty(N, 3 * 6912, device=DEV)
     dAs = torch.empty(N, 24, 12, device=DEV)
     lib.skin_bwd(a32, p32, C.vt, C.Wt, None, signs, scale, dPO, dAs, N)
