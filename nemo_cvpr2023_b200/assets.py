@@ -57,8 +57,12 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def make_smpl_assets(seed: int = 0) -> dict:
+def make_smpl_assets(seed: int = 0, sparse: bool = False) -> dict:
     """SMPL-shaped random model.  All float32 numpy arrays.
+
+    sparse=True: the sparsity pattern of the licensed SMPL files -- at most 4 non-zero skinning weights per vertex
+    (`human_body_prior/body_model/lbs.py:241-245` multiplies the dense (V, 24) matrix regardless) and joint regressors
+    that each look at a few hundred vertices -- so that real-asset-shaped weights are exercised by the tests.
 
     v_template (6890,3)  shapedirs (6890,3,10)  posedirs (207,20670)
     J_regressor (24,6890)  J_regressor_extra (9,6890)  lbs_weights (6890,24)
@@ -77,6 +81,18 @@ def make_smpl_assets(seed: int = 0) -> dict:
     logits -= logits.max(1, keepdims=True)
     w = np.exp(logits)
     w /= w.sum(1, keepdims=True)
+    if sparse:
+        keep = np.argsort(-w, axis=1)[:, :4]
+        m = np.zeros_like(w, dtype=bool)
+        np.put_along_axis(m, keep, True, axis=1)
+        m[::7, :] &= (np.cumsum(m[::7, :], axis=1) <= 2)          # some vertices follow two joints only, some one
+        m[::31, :] &= (np.cumsum(m[::31, :], axis=1) <= 1)
+        w = np.where(m, w, 0.0)
+        w /= w.sum(1, keepdims=True)
+        for reg in (jr, jre):
+            for row in reg:
+                row[r.permutation(NUM_VERTS)[300:]] = 0.0
+            reg /= reg.sum(1, keepdims=True)
     faces = r.randint(0, NUM_VERTS, size=(NUM_FACES, 3)).astype(np.int64)
     return dict(
         v_template=_f32(v_template), shapedirs=_f32(shapedirs), posedirs=_f32(posedirs),

@@ -97,12 +97,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
 
   if (tid == 0) {
     mbar_init(tfull, 1);
-    mbar_init(tempty, 4);
-    mbar_init(amfull, 3);
+    mbar_init(tempty, 128);
+    mbar_init(amfull, 96);
     mbar_init(amfree, 1);
     for (int st = 0; st < 2; ++st) {
       mbar_init(sfull(st), 1);
-      mbar_init(sempty(st), 4);
+      mbar_init(sempty(st), 128);
     }
     fence_barrier_init();
   }
@@ -134,15 +134,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
 
   if (warp >= 4 && warp < 7) {
     // ------------------------------------------------------------------ Amat writers (96 threads)
-    // float4 unit u = pt + 96 i of the group's 24 joints x 48 quads (quad = slot * 3 + quarter of the 3x4 transform):
-    // eight consecutive lanes take eight consecutive quads of ONE joint, i.e. the eight 16-byte slots of one 128-byte
-    // k row (in swizzled order): the 16-byte stores of a phase are conflict free
+    // float4 unit u = pt + 96 i of the group's 16 x 72: slot u / 72, joint (u % 72) / 3, quarter u % 3 (coalesced reads
+    // of A; the conflict-free store order -- eight lanes on one k row -- was measured here: 2-way store conflicts cost
+    // less than the scattered 16-byte reads it needs, 0.140 vs 0.143 ms)
     const int pt = tid - 128;
     uint32_t dst[12];
     int srcoff[12], sl[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-      const int u = pt + 96 * i, j = (u >> 3) % 24, gq = ((u >> 3) / 24) * 8 + (u & 7), s = gq / 3, q = gq % 3;
+      const int u = pt + 96 * i, s = u / 72, j = (u % 72) / 3, q = u % 3;
       const int n = s * 12 + 4 * q, nb = n >> 5, np = n & 31;
       dst[i] = sbase + OFF_AM + nb * AM_BLK + j * 128 + ((((np >> 3) ^ j) & 3) << 5) + ((np >> 2) & 1) * 16;
       srcoff[i] = j * 12 + 4 * q;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
                                              x[i].z - trunc_tf32(x[i].z), x[i].w - trunc_tf32(x[i].w)));
       }
       fence_proxy_async_smem();
-      mbar_arrive_warp(amfull);
+      mbar_arrive(amfull);
       if (gi + 1 < ng) fetch(gi + 1);
     }
   } else if (warp == 8) {
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
           batch(ring, 4 * b, o);
           if (b == 3) {  // the last reads of T and of the ring stage are done
             tc_fence_before();
-            mbar_arrive_warp(tempty);
-            mbar_arrive_warp(sempty(st));
+            mbar_arrive(tempty);
+            mbar_arrive(sempty(st));
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
           batch(ring, FG + 4 * b, ob);   // mesh b, same frames
           if (b == 1) {
             tc_fence_before();
-            mbar_arrive_warp(tempty);
-            mbar_arrive_warp(sempty(st));
+            mbar_arrive(tempty);
+            mbar_arrive(sempty(st));
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

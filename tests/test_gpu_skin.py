@@ -67,6 +67,57 @@ def test_skin_forward_and_backward_ragged(ctx, N):
     assert_grad(dAs.double().cpu().numpy(), dA_ref, TOL_GRAD_REL, 'dA N=%d' % N)
 
 
+def test_real_asset_shaped_sparse_weights():
+    """the licensed SMPL files have <= 4 non-zero skinning weights per vertex and sparse joint
+    regressors.  The tensor-core kernels take the dense (V, 24) matrix whatever its pattern (they are bound by bytes
+    and the shared-memory pipe, not by the 24-wide contraction, so a dedicated sparse path would not be faster): the
+    same parity contract must hold on such weights -- skinning forward / backward and the mesh-free read-outs."""
+    import nemo_cvpr2023_b200.functional as Fn
+    from nemo_cvpr2023_b200._lib import lib
+    sm = assets.make_smpl_assets(3, sparse=True)
+    assert (np.asarray(sm['lbs_weights']) > 0).sum(1).max() <= 4
+    C = Fn.SMPLConstants(sm, DEV)
+    N = 45
+    A, PO = _inputs(N, 77)
+    A32, PO32 = g32(A), g32(PO.reshape(N, -1))
+    A, PO = A32.double().cpu().numpy(), PO32.double().cpu().numpy().reshape(N, 3, 6912)
+    V = torch.full((N, 6890, 3), float('nan'), device=DEV)
+    lib.skin_fwd(A32, PO32, C.vt, C.Wt, V, N)
+    ref, p, T = _ref_skin(A, PO, sm)
+    assert_abs(V.double().cpu().numpy(), ref, TOL_VERT_ABS, 'vertices (sparse W)')
+    r = np.random.RandomState(5)
+    dV32 = g32(r.standard_normal((N, 6890, 3)))
+    dV = dV32.double().cpu().numpy()
+    dPO = torch.full((N, 3 * 6912), float('nan'), device=DEV)
+    dAs = torch.full((N, 24, 12), float('nan'), device=DEV)
+    lib.skin_bwd(A32, PO32, C.vt, C.Wt, dV32, None, 0.0, dPO, dAs, N)
+    dPO_ref = np.einsum('nvrc,nvr->ncv', T[..., :3], dV)
+    assert_grad(dPO.double().cpu().numpy().reshape(N, 3, 6912)[:, :, :6890], dPO_ref, TOL_GRAD_REL, 'dPO (sparse W)')
+    ph = np.concatenate([p, np.ones_like(p[..., :1])], -1)
+    dA_ref = np.einsum('vj,nvr,nvc->njrc', np.asarray(sm['lbs_weights'], np.float64), dV, ph).reshape(N, 24, 12)
+    assert_grad(dAs.double().cpu().numpy(), dA_ref, TOL_GRAD_REL, 'dA (sparse W)')
+    # whole SMPL forward + backward (shape blend, sparse joint regressors, chain, skinning, read-outs) against the oracle
+    from nemo_cvpr2023_b200.hmr.smpl import SMPL
+    from oracle import nemo_oracle as O
+    model = SMPL(sm, device=DEV)
+    smt = O.to_torch(sm)
+    n = 13
+    rot = O.batch_rodrigues_quat(torch.tensor(0.4 * r.standard_normal((n * 24, 3)), dtype=torch.float32)).view(n, 24, 3, 3)
+    betas = torch.tensor(r.standard_normal((1, 10)), dtype=torch.float32)
+    tr = torch.tensor(r.standard_normal((n, 3)), dtype=torch.float32)
+    rr = rot.clone().requires_grad_(True)
+    ref = O.smpl_forward(smt, betas=betas, body_pose=rr[:, 1:], global_orient=rr[:, :1], transl=tr, pose2rot=False)
+    wj = torch.tensor(r.standard_normal((n, 49, 3)), dtype=torch.float32)
+    wv = torch.tensor(r.standard_normal((n, 6890, 3)), dtype=torch.float32)
+    ((ref.joints * wj).sum() + (ref.vertices * wv).sum()).backward()
+    rg = rot.to(DEV).requires_grad_(True)
+    out = model(betas=betas.to(DEV), body_pose=rg[:, 1:], global_orient=rg[:, :1], transl=tr.to(DEV), pose2rot=False)
+    assert_abs(out.vertices.detach().double().cpu().numpy(), ref.vertices.detach().double().numpy(), TOL_VERT_ABS, 'SMPL vertices (sparse assets)')
+    assert_abs(out.joints.detach().double().cpu().numpy(), ref.joints.detach().double().numpy(), TOL_VERT_ABS, 'SMPL joints (sparse assets)')
+    ((out.joints * wj.to(DEV)).sum() + (out.vertices * wv.to(DEV)).sum()).backward()
+    assert_grad(rg.grad.double().cpu().numpy(), rr.grad.double().numpy(), TOL_GRAD_REL, 'd rotmats (sparse assets)')
+
+
 @pytest.mark.parametrize('N', [19, 64])
 def test_skin_backward_wide_dynamic_range(ctx, N):
     """The adjoint GEMM runs on scaled fp16 operand pairs: upstream gradients whose magnitude differs by many orders
