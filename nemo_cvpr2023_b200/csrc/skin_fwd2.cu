@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int n = n0 + 4 * b + q;
+            // (the three stride-12-byte stores were measured against a transpose through shared memory that writes
+            // one full 128-byte line per store: 0.154 ms against 0.140 -- the extra shared-memory traffic costs more)
             if (real && n <= last) {  // frame test is warp-uniform
               float* d = a.V + ((size_t)n * NV + v) * 3;
               __stcs(d, o[q][0]);
