@@ -66,6 +66,15 @@ int nemo_b200_gemm_tc2(const float* A, const float* B, const float* bias, float*
                        int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                        int act, const float* gate, int ldg, float gate_slope, int accumulate,
                        int splits, void* stream);
+/* C[M,N] = out_scale * ( (a_scale*A)[M,K] . (Bh + Bl)^T ) + bias   -- the pose-blend matmul of lbs (lbs.py:229-233) on fp16
+ * operand PAIRS (tcgen05.mma.kind::f16, K = 16: half the MMAs of 3xTF32 for the same 22 mantissa bits).  A (M, lda) fp32,
+ * scaled by the power of two a_scale and split on the fly; Bh, Bl (N, ldb) fp16, K-major: the hi / lo parts of
+ * b_scale * B^T, split ONCE by the caller (B = posedirs is a constant of the body model); out_scale = 1 / (a_scale *
+ * b_scale).  The caller guarantees |a_scale * A| < 65504 (the pose feature R - I lies in [-2, 2]: a_scale = 2^13).
+ * All pointers 16-byte aligned, lda % 4 == 0, ldb % 8 == 0, ldc % 4 == 0, N % 4 == 0 or ldc - N < 4. */
+int nemo_b200_gemm_h16(const float* A, const void* Bh, const void* Bl, const float* bias, float* C,
+                       int M, int N, int K, int lda, int ldb, int ldc, float a_scale, float out_scale,
+                       void* stream);
 /* same contract, always on the CUDA cores (fp32 FMA); the cross-check of the tensor-core path */
 int nemo_b200_gemm_simt(const float* A, const float* B, const float* bias, float* C,
                         int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,

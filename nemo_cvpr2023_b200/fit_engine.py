@@ -20,7 +20,7 @@ import torch
 
 from . import assets
 from ._lib import ADAM_OWNS_STEP, ADAM_SKIP, AdamSeg, adam_multi, lib, require_cuda
-from .functional import KP_LOSSES, NV, RBF_BASES, VP, SMPLConstants, gemm
+from .functional import KP_LOSSES, NV, RBF_BASES, VP, SMPLConstants, gemm, pose_blend
 
 LDY = 148      # row stride of the (N+1, 147) MLP output / its gradient: 16-byte rows for the TMA-fed GEMM
 LDF = 208      # row stride of the (N, 207) pose feature, same reason
@@ -195,6 +195,9 @@ _DP_DRY = bool(int(__import__('os').environ.get('NEMO_B200_DP_DRY', '0')))
 # ~50 us of the 9 MB all-reduce stay exposed either way), and the capture hung the 2-rank parity test once.  Default 0:
 # two graphs around one eager all-reduce.
 _DP_GRAPH_NCCL = bool(int(__import__('os').environ.get('NEMO_B200_DP_GRAPH_NCCL', '0')))
+# NEMO_B200_DP_SYMM=1: the shared gradient is reduced through NVSwitch multicast (symmetric memory, multimem.ld_reduce /
+# multimem.st) by ONE kernel inside the step graph instead of an eager NCCL all-reduce between two graphs
+_DP_SYMM = int(__import__('os').environ.get('NEMO_B200_DP_SYMM', '0'))
 
 
 class _Range:
@@ -330,6 +333,17 @@ class FitEngine:
         oh = off['learned_motion.rot_out.weight'][0]
         ot = off['phase_rbf.log_sigmas'][0] if self.D > 0 else self.g_motion.g.numel()
         self._dp_buckets = dict(head=(oh, ot), l4=(o4, oh), l2=(o2, o4), l0=(0, o2), tail=(ot, self.g_motion.g.numel()))
+        self._symm = None
+        if _DP_SYMM and self.world > 1 and not reduce_all:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            n = (self.g_motion.g.numel() + 1023) // 1024 * 1024
+            with torch.cuda.device(self.dev):
+                buf = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+                self._symm_hdl = symm_mem.rendezvous(buf, grp.group_name)
+            buf.zero_()
+            self._symm, self._symm_group = buf, grp.group_name
 
     def track_info(self, info):
         import weakref
@@ -364,6 +378,13 @@ class FitEngine:
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(ev)
             self._dp_handles.append(dist.all_reduce(self.g_motion.g[lo:hi], group=self.dp_group, async_op=True))
+
+    def _symm_allreduce(self):
+        """sum of the shared gradient over the ranks through the NVSwitch multicast address (graph-capturable)"""
+        g, n = self.g_motion.g, self.g_motion.g.numel()
+        self._symm[:n].copy_(g)
+        torch.ops.symm_mem.multimem_all_reduce_(self._symm, 'sum', self._symm_group)
+        g.copy_(self._symm[:n])
 
     def _dp_finish(self, plain=False):
         import torch.distributed as dist
@@ -495,7 +516,7 @@ class FitEngine:
             lib.pose_chain_fwd(R, None, 0, 0, None, w['J'], 0, C.parents, None, w['F'], LDF, A, JP, N)
         else:
             lib.pose_chain_fwd(None, aa, lda, 0, w['R'], w['J'], 0, C.parents, R, w['F'], LDF, A, JP, N)
-        gemm(w['F'], C.PD, PO, N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
+        pose_blend(w['F'], C, PO, N, LDF)
 
     def _joints_forward(self, w, N):
         """The main mesh of a step is consumed only through 25 joints: kinematic joints come
@@ -756,18 +777,21 @@ class FitEngine:
         key = (N, mode, bool(detach_pose), bool(self.training), bool(skip_lag), bool(self.compute_betas_grad),
                tuple((id(g), g.lr, g.wd, g.betas, g.eps, g.decoupled) for g in groups))
 
-        dp = self.world > 1 and not (_DP_GRAPH_NCCL and self.dp_overlap and not self.dp_defer)
+        symm = self.world > 1 and getattr(self, '_symm', None) is not None and not self.dp_defer
+        dp = self.world > 1 and not symm and not (_DP_GRAPH_NCCL and self.dp_overlap and not self.dp_defer)
 
         def body():
             # data parallel: the graph stops before the all-reduce (NCCL stays OUTSIDE the captured graphs: one eager
             # collective between the two replays; a second graph holds the optimisers)
             saved = self.dp_defer
-            self.dp_defer = self.dp_defer or dp
+            self.dp_defer = self.dp_defer or dp or symm
             try:
                 out = self.forward_backward(w['vi'], w['fi'], update=True, mode=mode, detach_pose=detach_pose,
                                             _indices_loaded=True)
             finally:
                 self.dp_defer = saved
+            if symm:
+                self._symm_allreduce()
             if not dp:      # one GPU, or the collectives are part of the graph (forward_backward has joined them)
                 self.optimizer_step(groups, skip_lag=skip_lag)
             return out
@@ -868,7 +892,7 @@ class FitEngine:
         V = None
         if want_vertices:
             V = torch.empty(N, NV, 3, device=self.dev)
-            gemm(w['F_m'], C.PD, w['PO_m'], N, 3 * VP, 207, LDF, 3 * VP, 3 * VP)
+            pose_blend(w['F_m'], C, w['PO_m'], N, LDF)
             lib.skin_fwd(w['A_m'], w['PO_m'], w['base'], C.Wt, V, N)
         j = torch.empty(N, 25, 3, device=self.dev)
         lib.joints_gather_fwd(w['JP'], w['JX'], ro['np'] + ro['nx'], ro['np'], self.map25, 25,

@@ -6,6 +6,8 @@ fallback (a CPU tensor raises).  The reference functions each op stands in for a
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -28,6 +30,21 @@ def _f32c(t):
 
 def _new(shape, like, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+_POSE_BLEND_H16 = bool(int(os.environ.get('NEMO_B200_POSEBLEND_H16', '1')))
+A_SCALE_H16 = float(2 ** 13)      # the pose feature R - I lies in [-2, 2]
+
+
+def pose_blend(F, C, PO, N, ldf):
+    """PO (N, 3VP) = F (N, 207; row stride ldf) @ posedirs (lbs.py:229-233) for ROTATION pose features (|R - I| <= 2):
+    the fp16-pair tensor-core kernel with the constant operand split once (`SMPLConstants.PDh / PDl`), half the MMAs of the
+    3xTF32 GEMM.  NEMO_B200_POSEBLEND_H16=0 keeps the 3xTF32 kernel."""
+    if _POSE_BLEND_H16 and C.PDh is not None:
+        lib.gemm_h16(F, C.PDh, C.PDl, None, PO, N, 3 * VP, 207, ldf, C.PDh.shape[1], 3 * VP, A_SCALE_H16,
+                     1.0 / (A_SCALE_H16 * C.pd_scale))
+    else:
+        gemm(F, C.PD, PO, N, 3 * VP, 207, ldf, 3 * VP, 3 * VP)
 
 
 def gemm(A, B, C, M, N, K, lda, ldb, ldc, transA=False, transB=False, bias=None, act=0, gate=None, ldg=0,
@@ -306,6 +323,17 @@ class SMPLConstants:
         self.Sp = planar(sd.permute(2, 0, 1)).to(dev).contiguous()
         self.PD = planar(pd.view(207, NV, 3)).to(dev).contiguous()
         self.basis = torch.cat([self.PD, self.Sp], 0).contiguous()
+        # posedirs^T as an fp16 PAIR (hi = rn16(x), lo = rn16(x - hi)) of 2^k posedirs, K-major (3VP, 224): the constant
+        # operand of the fp16-pair pose-blend GEMM (csrc/gemm_h16.cu); the largest entry lands in [2^13, 2^14)
+        pmax = float(self.PD.abs().max())
+        self.PDh = self.PDl = None
+        self.pd_scale = 1.0
+        if pmax > 0 and np.isfinite(pmax):
+            self.pd_scale = float(2.0 ** (13 - int(np.floor(np.log2(pmax)))))
+            x = torch.zeros(3 * VP, 224, device=dev)
+            x[:, :207] = self.PD.t() * self.pd_scale
+            self.PDh = x.half().contiguous()
+            self.PDl = (x - self.PDh.float()).half().contiguous()
         self.Jt = (jr.double() @ vt.double()).float().reshape(72).to(dev)
         self.JSt = torch.einsum('jv,vcl->ljc', jr.double(), sd.double()).float().reshape(self.num_betas, 72).to(dev).contiguous()
         wt = torch.zeros(24, VP)

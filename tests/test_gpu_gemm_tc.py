@@ -213,3 +213,33 @@ def test_gemm_tc2_epilogues_and_splitk(lib):
     lib.gemm_tc2(G(A2), G(B2), None, C, M2, N2, K2, K2, K2, 208, 0, 1, 0, None, 0, 0.0, 0, 0)
     ref = A2.astype(np.float64) @ B2.T.astype(np.float64)
     assert np.abs(npy(C)[:, :N2] - ref).max() / np.abs(ref).max() < 4e-6
+
+
+@pytest.mark.parametrize('M,N,K', [(4096, 20736, 207), (37, 20736, 207), (300, 1000, 64), (129, 260, 33)])
+def test_gemm_h16_pose_blend(lib, M, N, K):
+    """The fp16-pair pose-blend GEMM (csrc/gemm_h16.cu: tcgen05 kind::f16, constant operand split once) against
+    float64: A = rotation-like pose features in [-2, 2] with a wide spread of magnitudes, B = a posedirs-like constant;
+    ragged M / N / K."""
+    r = np.random.RandomState(M + N + K)
+    A = np.clip(r.standard_normal((M, K)) * 10.0 ** r.uniform(-4, 0, size=(M, K)), -2, 2).astype(np.float32)
+    A[:, ::17] = 0.0
+    B = (1e-3 * r.standard_normal((K, N)) * 10.0 ** r.uniform(-3, 0, size=(K, N))).astype(np.float32)
+    Ad, lda = pad_ld(A)
+    ldb = (K + 31) // 32 * 32
+    pmax = float(np.abs(B).max())
+    bs = 2.0 ** (13 - int(np.floor(np.log2(pmax))))
+    x = torch.zeros(N, ldb, device=DEV)
+    x[:, :K] = G(B).t() * bs
+    Bh = x.half().contiguous()
+    Bl = (x - Bh.float()).half().contiguous()
+    ldc = (N + 3) // 4 * 4
+    C = torch.full((M, ldc), float('nan'), device=DEV)
+    lib.gemm_h16(Ad, Bh, Bl, None, C, M, N, K, lda, ldb, ldc, float(2 ** 13), 1.0 / (2 ** 13 * bs))
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    got = npy(C)[:, :N]
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= 3e-6, 'rel-max error %.2e' % err
+    # row-wise: rows of tiny features keep their relative accuracy
+    rows = np.abs(ref).max(1) > 0
+    rerr = (np.abs(got - ref).max(1)[rows] / np.abs(ref).max(1)[rows]).max()
+    assert rerr <= 2e-5, 'worst row-relative error %.2e' % rerr

@@ -56,3 +56,19 @@ for name, M, N, K, ta, tb in SHAPES:
     err_s = ((C.double() - ref).abs().max() / ref.abs().max()).item()
     print('%-20s M=%5d N=%5d K=%5d  tc2 %.3f ms (%.1f)  tc %.3f ms (%.1f TFLOP/s fp32-equivalent)   simt %.3f ms (%.1f TFLOP/s)  rel-max err tc %.2e simt %.2e' % (
         name, M, N, K, t_t2, fl / t_t2 / 1e9, t_tc, fl / t_tc / 1e9, t_si, fl / t_si / 1e9, err, err_s))
+
+# the fp16-pair pose-blend kernel (csrc/gemm_h16.cu), same shape as 'pose-blend fwd'
+M, N, K = 4096, 20736, 207
+A = torch.randn(M, 208, device=dev).clamp_(-2, 2)
+B = 1e-3 * torch.randn(K, N, device=dev)
+bs = 2.0 ** (13 - int(torch.floor(torch.log2(B.abs().max()))))
+x = torch.zeros(N, 224, device=dev)
+x[:, :K] = B.t() * bs
+Bh = x.half().contiguous()
+Bl = (x - Bh.float()).half().contiguous()
+C = torch.empty(M, N, device=dev)
+t = timeit(lambda: lib.gemm_h16(A, Bh, Bl, None, C, M, N, K, 208, 224, N, float(2 ** 13), 1.0 / (2 ** 13 * bs)))
+ref = A[:, :K].double() @ B.double()
+err = ((C.double() - ref).abs().max() / ref.abs().max()).item()
+print('%-20s M=%5d N=%5d K=%5d  fp16-pair kernel %.3f ms (%.1f TFLOP/s fp32-equivalent)  rel-max err %.2e' % (
+    'pose-blend fwd h16', M, N, K, t, 2.0 * M * N * K / t / 1e9, err))
