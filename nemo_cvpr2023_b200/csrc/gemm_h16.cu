@@ -50,7 +50,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && BH_BYTES % 1024 == 0, "swizzled operand alignment");
 
 struct Params {
-  int M, N, K, mtiles, ntiles, kblocks, flush;
+  int M, N, K, mtiles, ntiles, kblocks, flush, splits;
   float a_scale, out_scale;
   const float* bias;
   float* C;
@@ -79,7 +79,8 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmBh,
-                                                             const __grid_constant__ CUtensorMap tmBl, const Params p) {
+                                                             const __grid_constant__ CUtensorMap tmBl,
+                                                             const __grid_constant__ CUtensorMap tmC, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = sbase + OFF_BARS;
@@ -109,8 +110,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32u(tmem_slot);
-  const int units = p.mtiles * p.ntiles;
+  // unit = (tile, k split): a long K (the dgrad, K = 20 736) is cut so that every SM has work; the partial tiles then
+  // leave through TMA reduce-add into the zeroed C
+  const int units = p.mtiles * p.ntiles * p.splits;
   constexpr uint32_t idesc = idesc_f16(BM, BN);
+  auto krange = [&](int split, int& kb0, int& kb1) {
+    kb0 = (int)((long long)split * p.kblocks / p.splits);
+    kb1 = (int)((long long)(split + 1) * p.kblocks / p.splits);
+  };
 
   if (warp < 4) {
     setmaxnreg_dec<40>();
@@ -119,8 +126,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_consta
       if (lane == 0) {
         uint32_t it = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-          const int mb = u % p.mtiles, nb = u / p.mtiles;
-          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int split = u % p.splits, tile = u / p.splits;
+          const int mb = tile % p.mtiles, nb = tile / p.mtiles;
+          int kb0, kb1;
+          krange(split, kb0, kb1);
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int s = it % STAGES;
             mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
             mbar_arrive_expect_tx(full(s), STAGE_BYTES);
@@ -138,10 +148,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_consta
         uint32_t it = 0, pc = 0;
         const uint32_t d = tmem_base;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-          for (int kc = 0; kc < p.kblocks; kc += p.flush, ++pc) {
+          int kb0, kb1;
+          krange(u % p.splits, kb0, kb1);
+          for (int kc = kb0; kc < kb1; kc += p.flush, ++pc) {
             if (pc > 0) mbar_wait(pempty, (pc - 1) & 1);   // the previous partial has been folded into registers
             tc_fence_after();
-            const int kce = min(kc + p.flush, p.kblocks);
+            const int kce = min(kc + p.flush, kb1);
             for (int kb = kc; kb < kce; ++kb, ++it) {
               const int s = it % STAGES;
               mbar_wait(conv(s), (it / STAGES) & 1);
@@ -174,7 +186,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_consta
     const float sc = p.a_scale;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+      int kb0, kb1;
+      krange(u % p.splits, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t sa = sbase + s * STAGE_BYTES;
         mbar_wait(full(s), (it / STAGES) & 1);
@@ -201,11 +215,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_consta
     const uint32_t rowo = lane * 128;
     uint32_t pc = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int mb = u % p.mtiles, nb = u / p.mtiles;
+      const int split = u % p.splits, tile = u / p.splits;
+      const int mb = tile % p.mtiles, nb = tile / p.mtiles;
+      int kb0, kb1;
+      krange(split, kb0, kb1);
       float acc[NC];
 #pragma unroll
       for (int j = 0; j < NC; ++j) acc[j] = 0.f;
-      for (int kc = 0; kc < p.kblocks; kc += p.flush, ++pc) {
+      for (int kc = kb0; kc < kb1; kc += p.flush, ++pc) {
         mbar_wait(pfull, pc & 1);
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + hc * NC;
@@ -236,13 +253,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_consta
             for (int c4 = 0; c4 < 8; ++c4) {
               const int j0 = rd * 64 + b * 32 + 4 * c4;
               float x[4] = {acc[j0] * os, acc[j0 + 1] * os, acc[j0 + 2] * os, acc[j0 + 3] * os};
-              if (p.bias) {
+              if (p.bias && split == 0) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) x[k] += (n0 + 4 * c4 + k < p.N) ? __ldg(p.bias + n0 + 4 * c4 + k) : 0.f;
               }
               sts128(box0 + b * BOX_BYTES + rowo + ((c4 ^ (lane & 7)) << 4), make_float4(x[0], x[1], x[2], x[3]));
             }
           }
+        }
+        if (p.splits > 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmC, box0, n_rd, m_base);
+            if (n_rd + 32 < p.N) tma_reduce_add_2d(&tmC, box0 + BOX_BYTES, n_rd + 32, m_base);
+            bulk_commit();
+            bulk_wait_read0();   // the boxes are reused by the next round / tile
+          }
+          __syncwarp();
+          continue;
         }
         // read the boxes back row-wise (eight lanes per 128-byte row, four rows per instruction), 16-byte stores
         __syncwarp();
@@ -263,6 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_h16(const __grid_consta
       }
     }
   }
+  if (warp >= 8 && lane == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -337,12 +367,17 @@ extern "C" int nemo_b200_gemm_h16(const float* A, const void* Bh, const void* Bl
   p.ntiles = cdiv(N, BN);
   p.kblocks = cdiv(K, BKS);
   p.flush = 8;   // k-blocks (of 32) accumulated in tensor memory before the fold into fp32 registers: 256 k values
-  CUtensorMap ta, tbh, tbl;
+  const int tiles = p.mtiles * p.ntiles, sms = num_sms();
+  p.splits = 1;
+  if (tiles < sms && !bias) p.splits = max(1, min(sms / tiles, p.kblocks / 8));
+  if (p.splits > 1) NB_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, s));
+  CUtensorMap ta, tbh, tbl, tc;
+  if (int rc = make_map(&tc, C, 4, N, M, ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map(&ta, A, 4, K, M, lda, BKS, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map(&tbh, Bh, 2, K, N, ldb, BKS, BN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   if (int rc = make_map(&tbl, Bl, 2, K, N, ldb, BKS, BN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-  const int grid = min(p.mtiles * p.ntiles, num_sms());
+  const int grid = min(tiles * p.splits, sms);
   NB_SET_SMEM_ONCE(k_gemm_h16, SMEM_BYTES);
-  k_gemm_h16<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tbh, tbl, p);
+  k_gemm_h16<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tbh, tbl, tc, p);
   NB_LAUNCH_CHECK("gemm_h16");
 }

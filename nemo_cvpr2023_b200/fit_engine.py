@@ -20,7 +20,7 @@ import torch
 
 from . import assets
 from ._lib import ADAM_OWNS_STEP, ADAM_SKIP, AdamSeg, adam_multi, lib, require_cuda
-from .functional import KP_LOSSES, NV, RBF_BASES, VP, SMPLConstants, gemm, pose_blend
+from .functional import KP_LOSSES, NV, RBF_BASES, VP, SMPLConstants, gemm, pose_blend, pose_blend_dgrad
 
 LDY = 148      # row stride of the (N+1, 147) MLP output / its gradient: 16-byte rows for the TMA-fed GEMM
 LDF = 208      # row stride of the (N, 207) pose feature, same reason
@@ -669,9 +669,10 @@ class FitEngine:
                      gate_slope=0.01)
                 gemm(w['dE1'], vp['W1e'], w['d_aa'], N, 72, H_VP, H_VP, 72, 72, accumulate=True)
             if full and w_vp:
-                lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, None, w['signs'], ls * w_vp / (N * NV * 3.0),
-                             w['dPO'], w['dAs'], N)
-                gemm(w['dPO'], C.PD, w['dF_o'], N, 207, 3 * VP, 3 * VP, 3 * VP, LDF, transB=True)
+                ss = ls * w_vp / (N * NV * 3.0)
+                lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, None, w['signs'], ss, w['dPO'], w['dAs'], N)
+                # |dPO| = |R^T dv| <= 3 |ss| (dv = +-ss or 0, blended rotation entries <= 1): known range, fp16-pair kernel
+                pose_blend_dgrad(w['dPO'], C, w['dF_o'], N, LDF, 4.0 * abs(ss))
                 lib.chain_bwd2(w['R_o'], w['J'], 0, C.parents, w['dAs'], None, None, w['dF_o'], LDF, w['dR_o'],
                                w['dJ'].zero_() if self.compute_betas_grad else None, N)
                 if self.compute_betas_grad:

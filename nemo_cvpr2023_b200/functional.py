@@ -47,6 +47,18 @@ def pose_blend(F, C, PO, N, ldf):
         gemm(F, C.PD, PO, N, 3 * VP, 207, ldf, 3 * VP, 3 * VP)
 
 
+def pose_blend_dgrad(dPO, C, dF, N, ldf, bound):
+    """dF (N, 207; row stride ldf) = dPO (N, 3VP) @ posedirs^T for an upstream gradient with a KNOWN bound |dPO| <= bound
+    (the vertex L1 of vposer_loss: dv = +-s or 0 and the blended rotation has entries <= 1, so |R^T dv| <= 3 s): the
+    fp16-pair kernel with split-K.  Anything else goes through the 3xTF32 GEMM."""
+    if _POSE_BLEND_H16 and C.PDh is not None and bound > 0 and np.isfinite(bound):
+        a_scale = float(2.0 ** (13 - int(np.ceil(np.log2(bound)))))
+        lib.gemm_h16(dPO, C.PDgh, C.PDgl, None, dF, N, 207, 3 * VP, 3 * VP, 3 * VP, ldf, a_scale,
+                     1.0 / (a_scale * C.pd_scale))
+    else:
+        gemm(dPO, C.PD, dF, N, 207, 3 * VP, 3 * VP, 3 * VP, ldf, transB=True)
+
+
 def gemm(A, B, C, M, N, K, lda, ldb, ldc, transA=False, transB=False, bias=None, act=0, gate=None, ldg=0,
          gate_slope=0.0, accumulate=False):
     """Raw C-ABI GEMM on device pointers/tensors (see nemo_b200_gemm)."""
@@ -334,6 +346,10 @@ class SMPLConstants:
             x[:, :207] = self.PD.t() * self.pd_scale
             self.PDh = x.half().contiguous()
             self.PDl = (x - self.PDh.float()).half().contiguous()
+            # the same pair in posedirs' own orientation (207, 3VP): K-major operand of the dgrad (K = 3VP)
+            y = self.PD * self.pd_scale
+            self.PDgh = y.half().contiguous()
+            self.PDgl = (y - self.PDgh.float()).half().contiguous()
         self.Jt = (jr.double() @ vt.double()).float().reshape(72).to(dev)
         self.JSt = torch.einsum('jv,vcl->ljc', jr.double(), sd.double()).float().reshape(self.num_betas, 72).to(dev).contiguous()
         wt = torch.zeros(24, VP)

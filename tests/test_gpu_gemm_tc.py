@@ -243,3 +243,24 @@ def test_gemm_h16_pose_blend(lib, M, N, K):
     rows = np.abs(ref).max(1) > 0
     rerr = (np.abs(got - ref).max(1)[rows] / np.abs(ref).max(1)[rows]).max()
     assert rerr <= 2e-5, 'worst row-relative error %.2e' % rerr
+
+
+def test_gemm_h16_split_k_dgrad(lib):
+    """the same kernel on the pose-blend dgrad shape: K = 20 736 cut over the SMs (split-K, TMA reduce-add into the zeroed
+    C), N = 207 in a 208-wide buffer, A = a bounded upstream gradient."""
+    M, N, K = 1031, 207, 20736
+    r = np.random.RandomState(5)
+    bound = 3.7e-7
+    A = (bound * np.clip(r.standard_normal((M, K)), -1, 1) * (r.uniform(size=(M, K)) > 0.3)).astype(np.float32)
+    B = (1e-3 * r.standard_normal((N, K))).astype(np.float32)            # posedirs' own orientation: (207, 3VP), K-major
+    bs = 2.0 ** (13 - int(np.floor(np.log2(float(np.abs(B).max())))))
+    y = G(B) * bs
+    Bh = y.half().contiguous()
+    Bl = (y - Bh.float()).half().contiguous()
+    a_scale = 2.0 ** (13 - int(np.ceil(np.log2(bound))))
+    C = torch.full((M, 208), float('nan'), device=DEV)
+    lib.gemm_h16(G(A), Bh, Bl, None, C, M, N, K, K, K, 208, float(a_scale), 1.0 / (a_scale * bs))
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    got = npy(C)[:, :N]
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= 3e-6, 'rel-max error %.2e' % err

@@ -72,3 +72,18 @@ ref = A[:, :K].double() @ B.double()
 err = ((C.double() - ref).abs().max() / ref.abs().max()).item()
 print('%-20s M=%5d N=%5d K=%5d  fp16-pair kernel %.3f ms (%.1f TFLOP/s fp32-equivalent)  rel-max err %.2e' % (
     'pose-blend fwd h16', M, N, K, t, 2.0 * M * N * K / t / 1e9, err))
+
+# ... and on the dgrad shape (K = 20 736, split-K)
+M, N, K = 4096, 207, 20736
+A = (1e-6 * torch.randn(M, K, device=dev)).clamp_(-4e-6, 4e-6)
+B = 1e-3 * torch.randn(N, K, device=dev)
+y = B * bs
+Bh = y.half().contiguous()
+Bl = (y - Bh.float()).half().contiguous()
+C = torch.empty(M, 208, device=dev)
+asc = 2.0 ** (13 + 18)
+t = timeit(lambda: lib.gemm_h16(A, Bh, Bl, None, C, M, N, K, K, K, 208, asc, 1.0 / (asc * bs)))
+ref = A.double() @ B.double().t()
+err = ((C[:, :N].double() - ref).abs().max() / ref.abs().max()).item()
+print('%-20s M=%5d N=%5d K=%5d  fp16-pair kernel %.3f ms (%.1f TFLOP/s fp32-equivalent)  rel-max err %.2e' % (
+    'pose-blend dgrad h16', M, N, K, t, 2.0 * M * N * K / t / 1e9, err))
