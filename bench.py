@@ -396,12 +396,14 @@ def _run_gpu(a, rank, local, world, dev):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, flush=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for _ in range(steps):
             fn()
+        if flush:
+            flush()
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
@@ -419,13 +421,29 @@ def _run_gpu(a, rank, local, world, dev):
 
         def e2e_step():
             multi.step([vi_h] * A, [fi_h] * A)
+
+        e2e_flush = None
     else:
         def dev_step():      # inputs resident in HBM, no host read-back; one CUDA-graph launch on one GPU
             eng.training = train
             eng.step_graph(vi_d, fi_d, mode='step')
 
-        def e2e_step():      # the public call: pinned host indices in, loss dict out
+        def e2e_blocking():  # the public call: pinned host indices in, loss dict out, the host waits for it
             model.step(vi_h, fi_h)
+
+        pending = []
+
+        def e2e_step():
+            # the same call with the read-back pipelined by one step, like a fit loop that logs: the losses of every step
+            # are copied to pinned host memory and READ by the host, those of step i while step i + 1 runs
+            out, _ = model.step(vi_h, fi_h, sync=False)
+            if pending:
+                pending.pop().result()
+            pending.append(out)
+
+        def e2e_flush():     # the last step's losses are read inside the timed region too
+            while pending:
+                pending.pop().result()
 
     cs = ClockSampler(local).start()
     warm = max(3, a.warmup)
@@ -435,10 +453,17 @@ def _run_gpu(a, rank, local, world, dev):
         l0 = lib.launches
         t_dev = timed(dev_step, a.steps)
         launches = (lib.launches - l0) // a.steps
+    t_e2e_blocking = None
+    if not multi:
+        for _ in range(2):
+            e2e_blocking()
+        t_e2e_blocking = timed(e2e_blocking, a.steps)
     for _ in range(2):
         e2e_step()
+    if e2e_flush:
+        e2e_flush()
     with cs.window():
-        t_e2e = timed(e2e_step, a.steps)
+        t_e2e = timed(e2e_step, a.steps, e2e_flush)
     kernels = count_kernels(dev_step)     # every rank: the step holds a collective
     if rank != 0:
         cs.stop()
@@ -463,7 +488,10 @@ def _run_gpu(a, rank, local, world, dev):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(a.config, world),
         'clocks': clocks,
         'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': int(A * 2 * N * 8),
-                'd2h_bytes_per_step': A * 9 * 4, 'ms_per_step': t_e2e / a.steps * 1e3},
+                'd2h_bytes_per_step': A * 9 * 4, 'ms_per_step': t_e2e / a.steps * 1e3,
+                'readback': ('blocking' if multi else 'every step\'s packed loss vector is copied to pinned host memory '
+                             'and read by the host one step later (model.step(..., sync=False) -> PendingLosses.result())'),
+                'blocking_ms_per_step': (t_e2e_blocking / a.steps * 1e3 if t_e2e_blocking else None)},
         'gpu_launches': int(kernels.get('kernels', launches)),
         'gpu_launches_detail': dict(kernels, repo_c_abi_count=int(launches)),
         'roofline': {'bound': 'hbm', 'kernel': 'k_skin_fwd2<0> + k_skin_bwd2<dV> (K7, vertices written, dV read: 5 streams/frame)',

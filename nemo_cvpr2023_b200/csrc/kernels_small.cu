@@ -1,5 +1,6 @@
 // K1 (motion-field input), K3 (rotations), K6 (kinematic chain), K7b (projection + keypoint loss),
 // K8 (GMM prior), VPoser KL, fused Adam: the latency-bound, per-frame part of the fit path.
+#include <cstdlib>
 #include "pathmath.cuh"
 #include "rotmath.cuh"
 
@@ -462,13 +463,29 @@ __device__ __forceinline__ float mono_y_lane(const float* __restrict__ sh, const
   for (int k = lane; k < K; k += 32) s += sigmoidf_(fmaxf(sc[k], 0.f) * (u - fmaxf(sh[k], 0.f)));
   return warp_sum(s) / (float)K;
 }
-__global__ void k_mono_norm(const float* __restrict__ shifts, const float* __restrict__ scales, int K,
-                            float* __restrict__ yn, int V) {
-  int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (v >= V) return;
-  float y0 = mono_y_lane(shifts + (size_t)v * K, scales + (size_t)v * K, K, 0.f, lane);
-  float y1 = mono_y_lane(shifts + (size_t)v * K, scales + (size_t)v * K, K, 1.f, lane);
-  if (lane == 0) { yn[3 * v] = y0; yn[3 * v + 1] = y1; yn[3 * v + 2] = y1 - y0 + 1e-6f; }
+// y(0), y(1) of every view's phase warp: one block per view (a warp per view walked its K nodes in K/32 dependent
+// rounds: 7 us of latency at the head of every step)
+__global__ void __launch_bounds__(128) k_mono_norm(const float* __restrict__ shifts, const float* __restrict__ scales,
+                                                   int K, float* __restrict__ yn, int V) {
+  __shared__ float red[2][4];
+  const int v = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float* sh = shifts + (size_t)v * K;
+  const float* sc = scales + (size_t)v * K;
+  float s0 = 0.f, s1 = 0.f;
+  for (int k = threadIdx.x; k < K; k += 128) {
+    const float a = fmaxf(sc[k], 0.f), b = fmaxf(sh[k], 0.f);
+    s0 += sigmoidf_(a * (0.f - b));
+    s1 += sigmoidf_(a * (1.f - b));
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) { red[0][w] = s0; red[1][w] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float y0 = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / (float)K;
+    const float y1 = ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) / (float)K;
+    yn[3 * v] = y0; yn[3 * v + 1] = y1; yn[3 * v + 2] = y1 - y0 + 1e-6f;
+  }
 }
 // one warp per sample; sample N (the extra row) is the phase-0 / zero-code input of trans_0 (:3755-3766)
 __global__ void k_embed_fwd(const float* __restrict__ raw, const int64_t* __restrict__ vi,
@@ -597,13 +614,13 @@ __global__ void __launch_bounds__(256) k_embed_bwd(const float* __restrict__ raw
       atomicAdd(dls + i, s);
     }
 }
-// adds the y(0), y(1) normaliser terms of the phase warp: one warp per view
-__global__ void k_mono_finish(const float* __restrict__ shifts, const float* __restrict__ scales, int K,
-                              const float* __restrict__ gy01, float* __restrict__ dsh, float* __restrict__ dsc, int V) {
-  int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (v >= V) return;
+// adds the y(0), y(1) normaliser terms of the phase warp: one block per view, one node per thread and round
+__global__ void __launch_bounds__(128) k_mono_finish(const float* __restrict__ shifts, const float* __restrict__ scales,
+                                                     int K, const float* __restrict__ gy01, float* __restrict__ dsh,
+                                                     float* __restrict__ dsc, int V) {
+  const int v = blockIdx.x;
   float g0 = gy01[2 * v], g1 = gy01[2 * v + 1];
-  for (int k = lane; k < K; k += 32) {
+  for (int k = threadIdx.x; k < K; k += 128) {
     float scv = scales[(size_t)v * K + k], shv = shifts[(size_t)v * K + k];
     float a = fmaxf(scv, 0.f), b = fmaxf(shv, 0.f);
     float s0 = sigmoidf_(a * (0.f - b)), s1 = sigmoidf_(a * (1.f - b));
@@ -619,7 +636,7 @@ extern "C" int nemo_b200_embed_fwd(const float* raw_phase, const int64_t* view_i
   NB_REQUIRE(raw_phase && view_idx && shifts && scales && X && warped && yn && K > 0 && N >= 0 && V > 0 && D >= 0 &&
                  C >= 0 && ldx >= (D > 0 ? D : 1) + C && (D == 0 || (centres && log_sigmas)) && (C == 0 || codes) &&
                  basis >= 0 && basis <= 10, "embed_fwd: bad args");
-  k_mono_norm<<<cdiv(V, 4), 128, 0, S(stream)>>>(shifts, scales, K, yn, V);
+  k_mono_norm<<<V, 128, 0, S(stream)>>>(shifts, scales, K, yn, V);
   NB_LAUNCH_CHECK_CONT("mono_norm");
   k_embed_fwd<<<cdiv(N + 1, 4), 128, 0, S(stream)>>>(raw_phase, view_idx, shifts, scales, K, centres, log_sigmas, D,
                                                      basis, codes, C, noise, X, ldx, warped, yn, N);
@@ -635,14 +652,20 @@ extern "C" int nemo_b200_embed_bwd(const float* raw_phase, const int64_t* view_i
                  (D == 0 || (centres && log_sigmas && dlog_sigmas)),
              "embed_bwd: bad args (at most 256 phase-network nodes, 32 instance-code entries)");
   NB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * V, S(stream)));
-  const int per_block = 64;
+  // samples per block (8 warps, a contiguous run each): 64 left 65 blocks for 148 SMs and eight dependent samples per
+  // warp -- measured at N = 4096: 0.046 ms (64), 0.033 (32), 0.029 (16).  NEMO_B200_EMBED_PB: measurement switch
+  static const int per_block = [] {
+    const char* e = getenv("NEMO_B200_EMBED_PB");
+    const int v = e ? atoi(e) : 16;
+    return (v == 8 || v == 16 || v == 32 || v == 64) ? v : 16;
+  }();
   size_t smem = sizeof(float) * 8 * (D > 0 ? D : 1);
   k_embed_bwd<<<cdiv(N + 1, per_block), 256, smem, S(stream)>>>(raw_phase, view_idx, shifts, scales, K, centres,
                                                                 log_sigmas, D, basis, C, warped, yn, dX, ldx,
                                                                 dlog_sigmas, dshifts, dscales, dcodes, scratch, N,
                                                                 per_block);
   NB_LAUNCH_CHECK_CONT("embed_bwd");
-  k_mono_finish<<<cdiv(V, 4), 128, 0, S(stream)>>>(shifts, scales, K, scratch, dshifts, dscales, V);
+  k_mono_finish<<<V, 128, 0, S(stream)>>>(shifts, scales, K, scratch, dshifts, dscales, V);
   NB_LAUNCH_CHECK("mono_finish");
 }
 
@@ -733,7 +756,7 @@ extern "C" int nemo_b200_monotonic_bwd(const float* x, const float* shifts, cons
     k_mono_bwd<<<cdiv(N, 4), 128, 0, S(stream)>>>(x, shifts, scales, K, dout, dx, dshifts, dscales, scratch, N);
     NB_LAUNCH_CHECK_CONT("monotonic_bwd");
   }
-  k_mono_finish<<<1, 32, 0, S(stream)>>>(shifts, scales, K, scratch, dshifts, dscales, 1);
+  k_mono_finish<<<1, 128, 0, S(stream)>>>(shifts, scales, K, scratch, dshifts, dscales, 1);
   NB_LAUNCH_CHECK("mono_finish");
 }
 

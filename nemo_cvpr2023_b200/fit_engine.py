@@ -14,6 +14,7 @@ Reference semantics reproduced (paths under /root/reference, file nemo/neural_mo
 from __future__ import annotations
 
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -26,6 +27,25 @@ LDY = 148      # row stride of the (N+1, 147) MLP output / its gradient: 16-byte
 LDF = 208      # row stride of the (N, 207) pose feature, same reason
 H_VP = 512     # VPoser hidden width
 L_VP = 32      # VPoser latent size
+
+
+class PendingLosses:
+    """The losses of a step whose device->host copy may still be in flight (`NemoV*.step(..., sync=False)`)."""
+
+    def __init__(self, host, event, norm, keys=None):
+        self._host, self._event, self._norm, self._keys, self._out = host, event, norm, keys, None
+
+    def done(self):
+        return self._out is not None or self._event.query()
+
+    def result(self):
+        """-> the loss_dict `step` returns (numpy float32 scalars); waits for this step's copy if it has not landed"""
+        if self._out is None:
+            self._event.synchronize()
+            ld = FitEngine.loss_dict_from_host(self._host.numpy().astype(np.float64), self._norm)
+            self._out = ld if self._keys is None else {k: ld[k] for k in self._keys}
+            self._host = self._event = None
+        return self._out
 
 
 class ParamGroup:
@@ -189,6 +209,9 @@ def fold_vposer(sd, device):
 
 _NVTX = bool(int(__import__('os').environ.get('NEMO_B200_NVTX', '0')))
 _DP_DRY = bool(int(__import__('os').environ.get('NEMO_B200_DP_DRY', '0')))
+# NEMO_B200_SIDE_SMALL=0 keeps the small independent kernels of a step (shape blend, GMM prior, 3D pose loss, VPoser-KL
+# backward, bias column sums) on the main stream instead of the side stream (measurement switch; default: side stream)
+_SIDE_SMALL = bool(int(__import__('os').environ.get('NEMO_B200_SIDE_SMALL', '1')))
 # experimental (NEMO_B200_DP_GRAPH_NCCL=1): data-parallel steps as ONE CUDA graph with the bucketed NCCL all-reduces
 # captured on the communication stream.  Measured on 2 GPUs: no gain (2.073 vs 2.076 ms/step -- the compute kernels are
 # persistent, one CTA per SM with ~200 KB of shared memory, so an NCCL kernel only becomes resident between them and the
@@ -553,11 +576,40 @@ class FitEngine:
             w['raw'].copy_(phases)
         w['zbuf'].zero_()
         use_noise = self.version >= 3 and self.training and a.code_noise > 0 and self.Cc > 0
-        with _Range('nemo.motion_forward'):
-            self._motion_forward(w, N, vi, w['raw'], use_noise)
-            self._shape(w)
         full = mode == 'step'
         need_2d = mode in ('step', 'opt_cam', 'cam_fit')
+        # fork: with both branches present (a full step that updates), the 2-D branch goes to the side stream
+        overlap = (self.overlap_2d and need_2d and mode == 'step' and update and not self.compute_betas_grad
+                   and lib.profile is None)
+        # ... and so do the small kernels that depend on nothing but the pose (or a finished gradient): on the main
+        # stream each of them is 7-55 us of a nearly empty GPU on the critical path (profiles/r02_launches_v3.csv).
+        # Not under the eager bucketed all-reduce, whose buckets follow the bias sums on the main stream.
+        side_small = overlap and _SIDE_SMALL and (self.world == 1 or self.dp_defer)
+        side = None
+        if overlap:
+            if self._side is None:
+                self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Event(), torch.cuda.Event())
+            side, ev_fork, ev_join = self._side
+        main = torch.cuda.current_stream()
+
+        def on_side(fn):
+            """queue fn on the side stream behind everything queued on the main stream so far -> its completion event"""
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fn()
+                done = torch.cuda.Event()
+                done.record(side)
+            return done
+
+        ev_shape = None
+        if side_small:
+            ev_shape = on_side(lambda: self._shape(w))
+        with _Range('nemo.motion_forward'):
+            self._motion_forward(w, N, vi, w['raw'], use_noise)
+            if not side_small:
+                self._shape(w)
         mode_id = KP_LOSSES.index(a.loss)
         red = 1 if mode == 'cam_fit' else 0
         cx, cy = float(self.IMG_D0 // 2), float(self.IMG_D1 // 2)   # (:3104-3106) height/2 is used as cx
@@ -600,23 +652,6 @@ class FitEngine:
                 w['dJ'].copy_(w['dJ_m'])
                 self._betas_grad(w, N, first=True, mesh=False)
 
-        # fork: with both branches present (a full step that updates), the 2-D branch goes to the side stream
-        overlap = (self.overlap_2d and need_2d and mode == 'step' and update and not self.compute_betas_grad
-                   and lib.profile is None)
-        if update:
-            self.g_zero.zero_()
-        if overlap:
-            if self._side is None:
-                self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Event(), torch.cuda.Event())
-            side, ev_fork, ev_join = self._side
-            ev_fork.record()
-            side.wait_event(ev_fork)
-            with torch.cuda.stream(side):
-                branch_2d_forward()
-                branch_2d_backward()
-                ev_join.record(side)
-        elif need_2d:
-            branch_2d_forward()
         w_vp = float(a.weight_vp_loss) if full else 0.0
         w_kl = float(a.weight_vp_z_loss) if full else 0.0
         w_gmm = float(a.weight_gmm_loss) if full else 0.0
@@ -624,7 +659,40 @@ class FitEngine:
         if mode == 'warmup':
             w_3d = 1.0
         w_inst = float(getattr(a, 'weight_instance_loss', 0.0)) if (self.version >= 3 and full and self.Cc) else 0.0
+
+        def pose_priors():
+            """GMM prior (:2758-2773: value and scaled gradient in one pass) and the 3D pose loss (:3870-3882): both read
+            the predicted axis-angle pose only and ADD their gradient into d_aa (zeroed before)"""
+            if full:
+                lib.gmm_prior_sym(w['aa'].view(-1)[3:], 72, self.gmm_means, self.gmm_psym, self.gmm_w,
+                                  self.gmm_means.shape[0], 69, w['ll'], ls * w_gmm / N,
+                                  w['d_aa'].view(-1)[3:] if update else None, 72, 1, N)
+                lib.colsum(w['ll'], acc[3:4], N, 1, 1, 1)
+            if w_3d or (self.version >= 3 and full and getattr(a, 'weight_3d_loss', 0.0)):
+                lib.pose3d_loss(w['aa'].view(-1)[3:], 72, vi, fi, self.hmr_theta, self.hmr_mask, 100.0, ls * w_3d,
+                                acc[2:3], w['d_aa'].view(-1)[3:] if update else None, 72, 1, N, 69, self.F)
+
+        def kl_backward():
+            vp = self.vp
+            gemm(w['dhead'], vp['Wh'], w['dE1'], N, H_VP, 2 * L_VP, 2 * L_VP, H_VP, H_VP, gate=w['E1'], ldg=H_VP,
+                 gate_slope=0.01)
+            gemm(w['dE1'], vp['W1e'], w['d_aa'], N, 72, H_VP, H_VP, 72, 72, accumulate=True)
+
+        if update:
+            self.g_zero.zero_()
         w['d_aa'].zero_()
+        ev_daa = None        # side stream: every addition to d_aa queued there has been made
+        if overlap:
+            ev_fork.record()
+            side.wait_event(ev_fork)
+            with torch.cuda.stream(side):
+                if side_small:
+                    pose_priors()
+                branch_2d_forward()
+                branch_2d_backward()
+                ev_join.record(side)
+        elif need_2d:
+            branch_2d_forward()
         if full:
             vp = self.vp
             # VPoser encode (mean) -> decode (:2779-2784)
@@ -639,18 +707,17 @@ class FitEngine:
             lib.rot6d_fwd(w['D3'], 6, w['Rdec'], 9, 1, N * 21)
             lib.rotmat2aa_fwd(w['Rdec'], 189, w['recon'], 69, 21, N * 21, 0)
             w['recon'][:, 63:].copy_(w['aa'][:, 66:72])
+            # the KL gradient (two small GEMMs that add into d_aa) needs nothing else: side stream, behind the pose priors
+            if side_small and update and w_kl:
+                ev_daa = on_side(kl_backward)
             # the two extra SMPL forwards of vposer_loss (:2787-2793): quaternion Rodrigues, shared global orient
+            if ev_shape is not None:
+                main.wait_event(ev_shape)
             self._lbs_forward(w, N, w['R_o'], w['PO_o'], w['A_o'], w['JPs'], aa=w['aa'].view(-1)[3:], lda=72)
             self._lbs_forward(w, N, w['R_r'], w['PO_r'], w['A_r'], w['JPs'], aa=w['recon'], lda=69)
             lib.skin_l1_fwd(w['A_o'], w['PO_o'], w['A_r'], w['PO_r'], w['base'], C.Wt, w['signs'], acc[0:1], N)
-            # GMM prior (:2758-2773): value and (scaled) gradient in one pass
-            lib.gmm_prior_sym(w['aa'].view(-1)[3:], 72, self.gmm_means, self.gmm_psym, self.gmm_w,
-                              self.gmm_means.shape[0], 69, w['ll'], ls * w_gmm / N,
-                              w['d_aa'].view(-1)[3:] if update else None, 72, 1, N)
-            lib.colsum(w['ll'], acc[3:4], N, 1, 1, 1)
-        if w_3d or (self.version >= 3 and full and getattr(a, 'weight_3d_loss', 0.0)):
-            lib.pose3d_loss(w['aa'].view(-1)[3:], 72, vi, fi, self.hmr_theta, self.hmr_mask, 100.0, ls * w_3d, acc[2:3],
-                            w['d_aa'].view(-1)[3:] if update else None, 72, 1, N, 69, self.F)
+        if not side_small:
+            pose_priors()
         if w_inst:
             code = self.g_inst.views['learned_instance_code']
             acc[5:6].copy_((code * code).mean().reshape(1))
@@ -663,11 +730,8 @@ class FitEngine:
             else:
                 dR.zero_()
                 w['dtr'].zero_()
-            if full and w_kl:
-                vp = self.vp
-                gemm(w['dhead'], vp['Wh'], w['dE1'], N, H_VP, 2 * L_VP, 2 * L_VP, H_VP, H_VP, gate=w['E1'], ldg=H_VP,
-                     gate_slope=0.01)
-                gemm(w['dE1'], vp['W1e'], w['d_aa'], N, 72, H_VP, H_VP, 72, 72, accumulate=True)
+            if full and w_kl and ev_daa is None:
+                kl_backward()
             if full and w_vp:
                 ss = ls * w_vp / (N * NV * 3.0)
                 lib.skin_bwd(w['A_o'], w['PO_o'], w['base'], C.Wt, None, w['signs'], ss, w['dPO'], w['dAs'], N)
@@ -677,20 +741,27 @@ class FitEngine:
                                w['dJ'].zero_() if self.compute_betas_grad else None, N)
                 if self.compute_betas_grad:
                     self._betas_grad(w, N, first=not need_2d, mesh=True)
+                # d_aa: the side stream's additions (pose priors, KL) come before the main stream's
+                if ev_daa is not None:
+                    main.wait_event(ev_daa)
+                elif side_small:
+                    main.wait_event(ev_join)
                 lib.rodrigues_bwd(w['aa'].view(-1)[3:], 72, w['dR_o'].view(-1)[9:], 216, w['d_aa'].view(-1)[3:], 72,
                                   23, 1, N * 23, 0)
                 if overlap:
-                    torch.cuda.current_stream().wait_event(ev_join)
+                    main.wait_event(ev_join)
                 dR[:, 0].add_(w['dR_o'][:, 0])
             elif overlap:
-                torch.cuda.current_stream().wait_event(ev_join)
+                main.wait_event(ev_join)
+                if ev_daa is not None:
+                    main.wait_event(ev_daa)
             # axis-angle outputs of the pose head -> rotation matrices -> 6D -> MLP output
             lib.rotmat2aa_bwd(w['R'], 9, w['d_aa'], 3, dR, 9, 1, 1, N * 24, 1)
             lib.rot6d_bwd(w['Y'], LDY, dR, 216, w['dY'], LDY, 24, 0, N * 24)
             # translation columns, pad column and the phase-0 row of dY (trans - trans_0, :3755-3766) in one launch
             lib.dy_tail(w['dtr'] if need_2d else None, w['dY'], LDY, N, w['dyscr'])
             with _Range('nemo.motion_backward'):
-                self._motion_backward(w, N, vi)
+                self._motion_backward(w, N, vi, on_side if side_small else None)
             if w_inst:
                 self.g_inst.gviews['learned_instance_code'].add_(
                     self.g_inst.views['learned_instance_code'], alpha=ls * 2.0 * w_inst / (self.V * self.Cc))
@@ -722,31 +793,43 @@ class FitEngine:
                  accumulate=True)
         gemm(w['dJ'], C.JSt, self.betas_grad, 1, 10, 72, 72, 72, 10, transB=True, accumulate=True)
 
-    def _motion_backward(self, w, N, vi):
+    def _motion_backward(self, w, N, vi, on_side=None):
+        """on_side: queue a bias column sum on the side stream behind the GEMM that produced its input (it returns the
+        completion event); None: on the main stream, where the eager data-parallel buckets follow it."""
         mv, gv = self.g_motion.views, self.g_motion.gviews
         Np, h, ind = N + 1, self.h, self.in_dim
         W = lambda i: mv['learned_motion.net.net.%d.weight' % i]
         gW = lambda i: gv['learned_motion.net.net.%d.weight' % i]
         gb = lambda i: gv['learned_motion.net.net.%d.bias' % i]
         dY = w['dY']
+        main = torch.cuda.current_stream()
+
+        def bias_sum(X, out, ncol, ld):
+            if on_side is None:
+                lib.colsum(X, out, Np, ncol, ld, 0)
+                return None
+            return on_side(lambda: lib.colsum(X, out, Np, ncol, ld, 0))
+
         gemm(dY, w['H3'], self.gWhead, 147, h, Np, LDY, h, h, transA=True)
         # d/d linear_out.bias of (trans - trans_0) cancels exactly (row N of dY is minus the column sum of the rows above
         # it): only the 144 rot_out columns are summed, the three linear_out.bias entries are never written and stay an
         # exact 0 like the reference's -- not summation-order noise that Adam would amplify into lr-sized steps
-        lib.colsum(dY, self.gbhead, Np, 144, LDY, 0)
+        bias_sum(dY, self.gbhead, 144, LDY)
         self._dp_bucket('head')
         gemm(dY, self.Whead, w['dHa'], Np, h, 147, LDY, h, h, gate=w['H3'], ldg=h)
         gemm(w['dHa'], w['H2'], gW(4), h, h, Np, h, h, h, transA=True)
-        lib.colsum(w['dHa'], gb(4), Np, h, h, 0)
+        ev_a = bias_sum(w['dHa'], gb(4), h, h)
         self._dp_bucket('l4')
         gemm(w['dHa'], W(4), w['dHb'], Np, h, h, h, h, h, gate=w['H2'], ldg=h)
         gemm(w['dHb'], w['H1'], gW(2), h, h, Np, h, h, h, transA=True)
-        lib.colsum(w['dHb'], gb(2), Np, h, h, 0)
+        bias_sum(w['dHb'], gb(2), h, h)
         self._dp_bucket('l2')
+        if ev_a is not None:
+            main.wait_event(ev_a)      # dHa is rewritten next: its column sum on the side stream must have read it
         gemm(w['dHb'], W(2), w['dHa'], Np, h, h, h, h, h, gate=w['H1'], ldg=h)
         gemm(w['dHa'], w['X'], self.g_motion.gpadded['learned_motion.net.net.0.weight'], h, ind, Np, h, self.ldx,
              self.ldx, transA=True)
-        lib.colsum(w['dHa'], gb(0), Np, h, h, 0)
+        ev_last = bias_sum(w['dHa'], gb(0), h, h)
         self._dp_bucket('l0')
         gemm(w['dHa'], self.g_motion.padded['learned_motion.net.net.0.weight'], w['dX'], Np, ind, h, h, self.ldx,
              self.ldx)
@@ -756,6 +839,8 @@ class FitEngine:
                       w['yn'], w['dX'], self.ldx, gv['phase_rbf.log_sigmas'] if self.D > 0 else None, gg['shifts'],
                       gg['scales'], self.g_inst.gviews['learned_instance_code'] if self.g_inst else None, w['gy01'], N,
                       self.V)
+        if ev_last is not None:
+            main.wait_event(ev_last)   # join: the side stream is in order, its last column sum is behind all the others
 
     @_on_device
     def step_graph(self, view_idx, frame_idx, mode='step', detach_pose=False, which=None, skip_lag=False):
@@ -863,6 +948,30 @@ class FitEngine:
             torch.distributed.all_reduce(vec, group=self.dp_group)
             vec /= self.world
         return self.loss_dict_from_host(vec.cpu().numpy().astype(np.float64), norm)
+
+    def loss_dict_async(self, w, norm, keys=None):
+        """The same read-back without blocking the host: the packed vector goes to a pinned slot with an asynchronous copy
+        and the caller gets a `PendingLosses` whose `result()` waits for THAT copy only -- a fit loop that reads the
+        losses of step i while step i + 1 runs never leaves the GPU idle (the blocking read costs ~50 us of a 1.9 ms
+        step: host-side dict building, index copies and the graph launch all sit behind the synchronisation)."""
+        vec = torch.cat([w['acc'], w['total']])
+        if self.world > 1:
+            torch.distributed.all_reduce(vec, group=self.dp_group)
+            vec /= self.world
+        if not hasattr(self, '_pin'):
+            self._pin = [torch.empty(9, dtype=torch.float32).pin_memory() for _ in range(8)]
+            self._pin_owner = [None] * 8
+            self._pin_i = 0
+        i = self._pin_i = (self._pin_i + 1) % 8
+        old = self._pin_owner[i]() if self._pin_owner[i] is not None else None
+        if old is not None:
+            old.result()              # still held eight steps later: take the values out before the slot is rewritten
+        self._pin[i].copy_(vec, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        out = PendingLosses(self._pin[i], ev, norm, keys)
+        self._pin_owner[i] = weakref.ref(out)
+        return out
 
     @staticmethod
     def loss_dict_from_host(host, norm):

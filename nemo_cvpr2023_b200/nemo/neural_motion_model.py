@@ -589,8 +589,12 @@ class MultiViewModel(nn.Module):
         f = torch.arange(self.num_frames).repeat(self.num_views)
         return v, f
 
-    def step(self, view_idx, frame_idx, update=True, full_batch=False):
-        """:3511-3598 / :3796-3909 -> (loss_dict of numpy scalars, info_dict)."""
+    def step(self, view_idx, frame_idx, update=True, full_batch=False, sync=True):
+        """:3511-3598 / :3796-3909 -> (loss_dict of numpy scalars, info_dict).
+        sync=False (not in the reference): the losses come back as a `PendingLosses` -- their device->host copy is queued
+        into pinned memory and `result()` gives the same dict once it has landed, so a loop that logs the losses of step
+        i while step i + 1 runs keeps the GPU busy.  A plateau scheduler (lr_factor < 1) needs the value at once and
+        waits for it either way."""
         e = self.engine
         if update and self.VERSION >= 3:
             self.training = True
@@ -607,11 +611,15 @@ class MultiViewModel(nn.Module):
             w, norm = e.forward_backward(vi, fi, update=update, mode='step')
             if update:
                 self._step_optimizers()
-        ld = e.loss_dict(w, norm)
-        loss_dict = {k: ld[k] for k in self._LOSS_KEYS}
+        if sync:
+            ld = e.loss_dict(w, norm)
+            loss_dict = {k: ld[k] for k in self._LOSS_KEYS}
+        else:
+            loss_dict = e.loss_dict_async(w, norm, self._LOSS_KEYS)
         if update and self.args.lr_factor < 1:
+            total = ld['total_loss'] if sync else loss_dict.result()['total_loss']
             for s in self.schedulers:
-                s.step(float(ld['total_loss']))
+                s.step(float(total))
         info_dict = _StepInfo(e, w, self.points2d_gt_all)
         self.training = False
         e.training = False

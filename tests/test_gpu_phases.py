@@ -174,3 +174,31 @@ def test_get_preds_given_phases_and_view_matches_get_preds_batch():
     ph = warped.view(-1, 1).clone().requires_grad_(True)
     m.get_preds_given_phases_and_view(vi, ph)[1].sum().backward()
     assert torch.isfinite(ph.grad).all() and float(ph.grad.abs().max()) > 0
+
+
+def test_step_with_pending_losses_equals_the_blocking_step():
+    """`step(..., sync=False)` queues the loss read-back into pinned memory (`PendingLosses`): read late, a step's
+    losses are the ones the blocking call returns (up to the summation order of the atomics), and a result that is
+    still held when its pinned slot comes round again (8 in rotation) keeps its values"""
+    from nemo_cvpr2023_b200.fit_engine import PendingLosses
+    _, _, ma, r = _pair()
+    _, _, mb, _ = _pair()
+    vi, fi = torch.tensor(r.randint(0, 4, 40)), torch.tensor(r.randint(0, 12, 40))
+    first_blocking = ma.step(vi, fi)[0]
+    pending = []
+    for _ in range(12):
+        out, info = mb.step(vi, fi, sync=False)
+        assert isinstance(out, PendingLosses)
+        pending.append(out)
+    res = [p.result() for p in pending]
+    assert all(p.done() for p in pending)
+    assert set(res[0]) == set(first_blocking)
+    for k in first_blocking:
+        assert_rel(float(res[0][k]), float(first_blocking[k]), TOL_LOSS_REL, 'first step ' + k)
+    totals = [float(x['total_loss']) for x in res]
+    assert all(np.isfinite(totals)) and len(set(totals)) > 1     # every step has its own values
+    # no update: the same forward read both ways
+    a = mb.step(vi, fi, update=False)[0]
+    b = mb.step(vi, fi, update=False, sync=False)[0].result()
+    for k in a:
+        assert_rel(float(b[k]), float(a[k]), TOL_LOSS_REL, 'no update ' + k)
