@@ -322,6 +322,16 @@ typedef struct nemo_b200_adam_seg {
 } nemo_b200_adam_seg;
 int nemo_b200_adam_multi(const nemo_b200_adam_seg* segs, int nseg, int* ticket, void* stream);
 
+/* ---------------------------------------------------------------- data-parallel gradient sum over peer memory
+ * The reference back-propagates ONE loss over all video instances (nemo/neural_motion_model.py:3511-3598); with the
+ * instances sharded over the GPUs of a node the shared MotionNet + RBF gradient is the sum of the ranks' (SURVEY.md
+ * 8(e)).  bufs: HOST array of `world` device pointers, entry r = rank r's symmetric buffer as mapped into this process
+ * (n data floats followed, at float offset sig_off >= n, by a 64-word signal area zeroed once before the first call);
+ * src / dst: the local gradient (may alias).  Three kernels on `stream` (capturable): stage, reduce slice `rank` of
+ * every buffer in rank order and write it to every buffer, copy out.  Every rank of the group must make the same calls. */
+int nemo_b200_p2p_allreduce(const void* const* bufs, int rank, int world, const float* src, float* dst, size_t n,
+                            size_t sig_off, void* stream);
+
 /* small utilities used by the host mirror */
 /* out = dy * act'(y) for y = act(.), act 1 relu / 2 leaky_relu(0.01) */
 int nemo_b200_act_bwd(const float* dy, const float* y, float* out, size_t n, int act, void* stream);

@@ -43,7 +43,7 @@ def parse_header(path=HEADER):
 
 
 # kernels enqueued per C-ABI call when it is not exactly one
-_KERNELS_PER_CALL = {'embed_fwd': 2, 'embed_bwd': 2, 'monotonic_bwd': 2, 'readout_bwd': 2, 'last_error': 0, 'version': 0, 'sm_arch': 0}
+_KERNELS_PER_CALL = {'p2p_allreduce': 3, 'embed_fwd': 2, 'embed_bwd': 2, 'monotonic_bwd': 2, 'readout_bwd': 2, 'last_error': 0, 'version': 0, 'sm_arch': 0}
 
 
 class _Lib:

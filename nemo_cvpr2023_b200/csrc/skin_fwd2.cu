@@ -372,6 +372,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
       mbar_wait(tfull, gi & 1);
       tc_fence_after();
       if (MODE == 0) {
+        // (the three stride-12-byte stores per frame were measured against a transpose through shared memory that writes
+        // one full 128-byte line per store: 0.154 ms against 0.140 -- the extra shared-memory traffic costs more)
+        // Fast path: the group lies inside the batch and the tile inside the mesh (everything but the last group / the
+        // last tile) -- no per-frame or per-thread test between the stores, one base pointer per group and constant
+        // frame offsets; with the tests inside, every store re-materialised its descriptor and took two branches.
+        const bool inside = (n0 + SL - 1 <= last) && (v0 + TILE_V <= NV);   // block-uniform
+        float* const dg = a.V + ((size_t)n0 * NV + v) * 3;
 #pragma unroll 1
         for (int b = 0; b < 4; ++b) {
           float o[4][3];
@@ -381,16 +388,22 @@ __global__ void __launch_bounds__(THREADS, 2) k_skin_fwd2(const __grid_constant_
             mbar_arrive(tempty);
             mbar_arrive(sempty(st));
           }
+          float* const db = dg + (size_t)b * (4 * NV * 3);
+          if (inside) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = n0 + 4 * b + q;
-            // (the three stride-12-byte stores were measured against a transpose through shared memory that writes
-            // one full 128-byte line per store: 0.154 ms against 0.140 -- the extra shared-memory traffic costs more)
-            if (real && n <= last) {  // frame test is warp-uniform
-              float* d = a.V + ((size_t)n * NV + v) * 3;
-              __stcs(d, o[q][0]);
-              __stcs(d + 1, o[q][1]);
-              __stcs(d + 2, o[q][2]);
+            for (int q = 0; q < 4; ++q) {
+              __stcs(db + q * (NV * 3), o[q][0]);
+              __stcs(db + q * (NV * 3) + 1, o[q][1]);
+              __stcs(db + q * (NV * 3) + 2, o[q][2]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (real && n0 + 4 * b + q <= last) {
+                __stcs(db + q * (NV * 3), o[q][0]);
+                __stcs(db + q * (NV * 3) + 1, o[q][1]);
+                __stcs(db + q * (NV * 3) + 2, o[q][2]);
+              }
             }
           }
         }

@@ -219,7 +219,9 @@ _SIDE_SMALL = bool(int(__import__('os').environ.get('NEMO_B200_SIDE_SMALL', '1')
 # two graphs around one eager all-reduce.
 _DP_GRAPH_NCCL = bool(int(__import__('os').environ.get('NEMO_B200_DP_GRAPH_NCCL', '0')))
 # NEMO_B200_DP_SYMM=1: the shared gradient is reduced through NVSwitch multicast (symmetric memory, multimem.ld_reduce /
-# multimem.st) by ONE kernel inside the step graph instead of an eager NCCL all-reduce between two graphs
+# multimem.st) by torch's kernel inside the step graph instead of an eager NCCL all-reduce between two graphs (measured
+# slower than NCCL).  NEMO_B200_DP_SYMM=2: this library's own peer-memory reduction (csrc/allreduce_p2p.cu: stage,
+# reduce-scatter + all-gather through P2P loads / stores, copy out) inside the step graph.
 _DP_SYMM = int(__import__('os').environ.get('NEMO_B200_DP_SYMM', '0'))
 
 
@@ -363,10 +365,18 @@ class FitEngine:
             grp = group if group is not None else dist.group.WORLD
             n = (self.g_motion.g.numel() + 1023) // 1024 * 1024
             with torch.cuda.device(self.dev):
-                buf = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+                buf = symm_mem.empty(n + 64, dtype=torch.float32, device=self.dev)   # + the signal area of the P2P kernels
                 self._symm_hdl = symm_mem.rendezvous(buf, grp.group_name)
             buf.zero_()
             self._symm, self._symm_group = buf, grp.group_name
+            if _DP_SYMM == 2:
+                import ctypes
+                hdl = self._symm_hdl
+                assert hdl.world_size == self.world and self.g_motion.g.numel() % 4 == 0
+                self._p2p_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+                self._p2p = (ctypes.addressof(self._p2p_ptrs), int(hdl.rank), n)
+                torch.cuda.synchronize(self.dev)
+                dist.barrier(group=grp)          # every rank's signal area is zero before anybody signals
 
     def track_info(self, info):
         import weakref
@@ -405,8 +415,13 @@ class FitEngine:
     def _symm_allreduce(self):
         """sum of the shared gradient over the ranks through the NVSwitch multicast address (graph-capturable)"""
         g, n = self.g_motion.g, self.g_motion.g.numel()
+        if getattr(self, '_p2p', None) is not None:
+            if not _DP_DRY:
+                ptrs, rank, sig_off = self._p2p
+                lib.p2p_allreduce(ptrs, rank, self.world, g, g, n, sig_off)
+            return
         self._symm[:n].copy_(g)
-        torch.ops.symm_mem.multimem_all_reduce_(self._symm, 'sum', self._symm_group)
+        torch.ops.symm_mem.multimem_all_reduce_(self._symm[:(n + 1023) // 1024 * 1024], 'sum', self._symm_group)
         g.copy_(self._symm[:n])
 
     def _dp_finish(self, plain=False):

@@ -84,10 +84,13 @@ def _local_name(k, views):
 
 
 @pytest.mark.timeout(240)
-@pytest.mark.parametrize('V', [8, 1])
-def test_two_ranks_equal_one_gpu(tmp_path, V):
+@pytest.mark.parametrize('V,symm', [(8, 0), (1, 0), (8, 2)])
+def test_two_ranks_equal_one_gpu(tmp_path, monkeypatch, V, symm):
+    """symm = 2: the shared gradient is summed by this library's peer-memory kernels inside the step graph
+    (csrc/allreduce_p2p.cu, NEMO_B200_DP_SYMM=2) instead of NCCL"""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs')
+    monkeypatch.setenv('NEMO_B200_DP_SYMM', str(symm))    # read by the spawned ranks when they import the engine
     from nemo_cvpr2023_b200.nemo import neural_motion_model as nmm
     from nemo_cvpr2023_b200.nemo.multi_view_sequence import SyntheticMultiViewSequence
     world = 2
