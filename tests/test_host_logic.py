@@ -95,3 +95,33 @@ def test_adam_segment_table():
     assert sum(s.n for s in segs) == g.p.numel()
     plain = fe.ParamGroup([('learned_cameras', (8, 9))], 'cpu', 0.1)
     assert plain.ranges() == [(0, 72, False)] and plain.segments()[0].flags == ADAM_OWNS_STEP
+
+
+def test_pending_losses_unpacks_the_packed_vector_once():
+    """`step(..., sync=False)`: `PendingLosses.result()` waits for ITS copy's event, turns the packed [acc(8) | total]
+    vector into the loss_dict of `step` (normalisers applied, requested keys only), and keeps the values after the pinned
+    slot has been rewritten"""
+    class Ev:
+        waited = 0
+
+        def synchronize(self):
+            Ev.waited += 1
+
+        def query(self):
+            return False
+
+    host = torch.tensor([6.0, 8.0, 0.25, 10.0, 3.0, 0.5, 0.0, 0.0, 42.0])
+    norm = np.asarray([0.5, 0.25, 1.0, 0.1, 1.0, 1.0, 0.0, 0.0])
+    keys = ['kp_loss', 'gmm_loss', 'vp_recon_loss', 'vp_kl_loss', 'total_loss']
+    p = fe.PendingLosses(host, Ev(), norm, keys)
+    assert not p.done()
+    out = p.result()
+    assert Ev.waited == 1 and p.done()
+    assert list(out) == keys
+    assert float(out['kp_loss']) == 3.0 and float(out['gmm_loss']) == 1.0 and float(out['vp_recon_loss']) == 3.0
+    assert float(out['vp_kl_loss']) == 2.0 and float(out['total_loss']) == 42.0
+    assert all(v.dtype == np.float32 for v in out.values())
+    host.fill_(-1.0)                       # the slot is reused by a later step
+    assert p.result() is out and float(p.result()['total_loss']) == 42.0 and Ev.waited == 1
+    full = fe.PendingLosses(torch.arange(9.0), Ev(), norm).result()
+    assert set(full) == {'kp_loss', 'vp_recon_loss', 'vp_kl_loss', 'gmm_loss', 'loss_3d', 'instance_loss', 'total_loss'}
