@@ -343,6 +343,10 @@ def run_gpu(a):
         _run_gpu(a, rank, local, world, dev)
     finally:
         if world > 1:
+            # NCCL_DEBUG=INFO: the communicator's teardown messages ("Destroy COMPLETE", every rank) must not follow the
+            # JSON line on stdout
+            sys.stdout.flush()
+            os.dup2(2, 1)
             torch.distributed.destroy_process_group()
 
 
